@@ -1,0 +1,174 @@
+/*
+ * pglb.h -- C-ABI of libpglb.so: the B200 (sm_100a) send/recv message-passing path
+ * behind PGL's Graph.send/recv API.
+ *
+ * The reference (PaddlePaddle/PGL @ 6dbb47c) has no native boundary of its own on this
+ * path: it is Python over Paddle's operator API plus one Cython module.  Every entry point
+ * below therefore names the reference call site(s) it replaces (paths relative to the
+ * reference root).  See INTEGRATION.md for the reference-side binding.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no torch / CUDA C++ types.  `stream` is a
+ *    cudaStream_t passed as void* (NULL = legacy default stream).
+ *  - All device entry points are asynchronous on `stream`, re-entrant and thread-safe; the
+ *    library never allocates or frees device memory and keeps no pointer past the call.
+ *    Scratch space is caller-owned: query with the matching *_ws() and pass (ws, ws_bytes).
+ *  - Index tensors are int64 (PGL mandates int64 edges: pgl/graph.py:130-135), features
+ *    are float32 row-major with an explicit leading dimension where noted.
+ *  - Return value: 0 = PGLB_OK; <0 = argument error (no device work was enqueued);
+ *    >= PGLB_CUDA_ERR_BASE = PGLB_CUDA_ERR_BASE + cudaError_t.  pglb_last_error() returns a
+ *    thread-local, human-readable description of the last non-zero return.
+ *  - No C++ exception crosses this boundary.
+ */
+#ifndef PGLB_H_
+#define PGLB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGLB_VERSION 100 /* 0.1.0 */
+
+#define PGLB_OK 0
+#define PGLB_EINVAL (-1)    /* null pointer / negative size / unknown enum */
+#define PGLB_ESHAPE (-2)    /* inconsistent sizes */
+#define PGLB_EWORKSPACE (-3) /* workspace too small or misaligned */
+#define PGLB_EUNSUPPORTED (-4)
+#define PGLB_ENOLIB (-5)    /* optional host dependency (METIS) not loadable */
+#define PGLB_CUDA_ERR_BASE 1000
+
+/* reduce_op of send_u_recv / send_ue_recv / segment_* (pgl/graph.py:856-857, pgl/math.py:34-46) */
+#define PGLB_REDUCE_SUM 0
+#define PGLB_REDUCE_MEAN 1
+#define PGLB_REDUCE_MAX 2
+#define PGLB_REDUCE_MIN 3
+
+/* message_op of send_ue_recv / send_uv (pgl/graph.py:923-927,958-962); COPY = no edge operand */
+#define PGLB_MSG_COPY 0
+#define PGLB_MSG_ADD 1
+#define PGLB_MSG_SUB 2
+#define PGLB_MSG_MUL 3
+#define PGLB_MSG_DIV 4
+
+/* how the second operand's row broadcasts against the D = H*Dh output columns */
+#define PGLB_BCAST_FULL 0   /* y row has D values                      */
+#define PGLB_BCAST_HEAD 1   /* y row has H values, y[c / Dh]  ([E,H,1] against [N,H,Dh]) */
+#define PGLB_BCAST_SCALAR 2 /* y row has 1 value   ([E] or [E,1])       */
+
+int pglb_version(void);
+const char *pglb_last_error(void);
+/* number of kernels this library has launched in the calling process (bench "gpu_launches") */
+int64_t pglb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * CSR build on the device.  Replaces EdgeIndex.from_edges (pgl/utils/edge_index.py:38-58;
+ * tensor branch :43-54 = scatter-count + argsort + 2 gathers + cumsum) and is bit-identical
+ * to the numpy branch's graph_kernel.build_index (pgl/graph_kernel.pyx:59-88): stable, i.e.
+ * ascending edge id inside every bucket.
+ *   u, v         : int64 device pointers, element i at u[i*u_stride] (so edges[:,1] of an
+ *                  [E,2] array is (edges+1, stride 2) -- no strided copies as in
+ *                  pgl/graph.py:859)
+ *   degree[N], indptr[N+1], sorted_u[E], sorted_v[E], sorted_eid[E] : int64 outputs
+ * ---------------------------------------------------------------------------------- */
+int pglb_csr_build_ws(int64_t num_edges, int64_t num_nodes, size_t *ws_bytes);
+int pglb_csr_build(const int64_t *u, int64_t u_stride, const int64_t *v, int64_t v_stride,
+                   int64_t num_edges, int64_t num_nodes, int64_t *degree, int64_t *indptr,
+                   int64_t *sorted_u, int64_t *sorted_v, int64_t *sorted_eid, void *ws,
+                   size_t ws_bytes, void *stream);
+
+/* Host twin of the above for numpy-mode graphs (EdgeIndex numpy branch,
+ * pgl/utils/edge_index.py:56-57 -> pgl/graph_kernel.pyx:59-88).  Blocking, host pointers. */
+int pglb_build_index_host(const int64_t *u, int64_t u_stride, const int64_t *v,
+                          int64_t v_stride, int64_t num_edges, int64_t num_nodes,
+                          int64_t *degree, int64_t *indptr, int64_t *sorted_u,
+                          int64_t *sorted_v, int64_t *sorted_eid);
+
+/* segment ids of a CSR: replaces Graph.get_segment_ids -> unique_segment
+ * (pgl/graph.py:1397-1407, pgl/utils/helper.py:156-160; paddle.unique(return_inverse)).
+ *   uniq_ind[K]   = rows with degree > 0 (ascending), segment_ids[E] = dense id per slot.
+ *   num_uniq      : device int64 scalar that receives K.
+ *   ws >= pglb_segment_ids_ws bytes. */
+int pglb_segment_ids_ws(int64_t num_nodes, size_t *ws_bytes);
+int pglb_segment_ids(const int64_t *indptr, int64_t num_nodes, int64_t num_edges,
+                     int64_t *uniq_ind, int64_t *segment_ids, int64_t *num_uniq, void *ws,
+                     size_t ws_bytes, void *stream);
+
+/* sorted segment ids [E] -> indptr[K+1] (used by segment_* below; K = ids[E-1]+1, caller-known) */
+int pglb_segment_indptr(const int64_t *segment_ids, int64_t num_edges, int64_t num_segments,
+                        int64_t *indptr, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Node-parallel CSR aggregation  out[d] = reduce_{slot j in row d} msg(j)   (K1/K2/K4)
+ *   msg(j) = x[cols[j]]                       (msg_op = COPY)
+ *          = x[cols[j]] (op) y[eid[j]]        (ADD/SUB/MUL/DIV, y broadcast per y_bcast)
+ * Replaces paddle.geometric.send_u_recv / send_ue_recv as called at pgl/graph.py:860,886,
+ * 930 (COO + atomics in the reference; here a cached dst-CSR, one writer per row,
+ * summation in ascending edge id = the reference CPU loop's order), the legacy
+ * helper.graph_send_recv (pgl/utils/helper.py:163-210) and, with cols == NULL (slot j
+ * reads row j), paddle.geometric.segment_{sum,mean,max,min} (pgl/math.py:36-42).
+ *   indptr[n_dst+1], cols[E] (nullable), eid[E] (nullable: y indexed by slot)
+ *   x  [n_src, ldx] (first D columns used), y per y_bcast (nullable iff COPY), row stride ldy
+ *   out[n_dst, ldo]; rows without a message are 0 for every reduce_op; MEAN divides by the
+ *   row's slot count.
+ *   scale_src[n_src] / scale_dst[n_dst] (nullable): msg *= scale_src[cols[j]] before the
+ *   reduce, out[d] *= scale_dst[d] after it (GCNConv's two norm multiplies, conv.py:242,250)
+ *   D = H * Dh output columns; head_dim = Dh (only used by PGLB_BCAST_HEAD).
+ *   max_degree_hint : max row length if the caller knows it (skips the hub pass when
+ *   small), or -1.
+ * ---------------------------------------------------------------------------------- */
+int pglb_spmm_csr_ws(int64_t n_dst, int64_t num_edges, int64_t D, size_t *ws_bytes);
+int pglb_spmm_csr_f32(const int64_t *indptr, const int64_t *cols, const int64_t *eid,
+                      const float *x, int64_t ldx, const float *y, int64_t ldy, int y_bcast,
+                      float *out, int64_t ldo, int64_t n_dst, int64_t n_src,
+                      int64_t num_edges, int64_t D, int64_t head_dim, int msg_op,
+                      int reduce_op, const float *scale_src, const float *scale_dst,
+                      int64_t max_degree_hint, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Edge-parallel ops
+ * ---------------------------------------------------------------------------------- */
+/* out[e] = x[src[e]] (op) y[dst[e]] ; replaces paddle.geometric.send_uv (pgl/graph.py:965).
+ * src/dst strided like pglb_csr_build.  x [n_src, D], y [n_dst, D], out [E, D]. */
+int pglb_send_uv_f32(const float *x, const float *y, const int64_t *src, int64_t src_stride,
+                     const int64_t *dst, int64_t dst_stride, int64_t num_edges, int64_t D,
+                     int msg_op, float *out, void *stream);
+
+/* out[i] = x[index[i]] ; paddle.gather(axis=0) at pgl/utils/op.py:45, pgl/message.py:157,
+ * pgl/math.py:219,223.  index strided. */
+int pglb_gather_rows_f32(const float *x, int64_t ldx, const int64_t *index,
+                         int64_t index_stride, int64_t num_rows, int64_t D, float *out,
+                         int64_t ldo, void *stream);
+/* out[index[i]] = x[i] (unique indices) ; paddle.scatter(overwrite=True) at
+ * pgl/graph.py:830, pgl/nn/functional/graph_op.py:122. */
+int pglb_scatter_rows_f32(const float *x, int64_t ldx, const int64_t *index,
+                          int64_t num_rows, int64_t D, float *out, int64_t ldo,
+                          void *stream);
+
+/* Per-row softmax over CSR rows, H columns; replaces pgl.math.segment_softmax
+ * (pgl/math.py:216-224: 7 ops) and, with eid != NULL, GF.edge_softmax
+ * (pgl/nn/functional/graph_op.py:117-123): slot j reads logits[eid[j]] and writes
+ * out[eid[j]] (original edge order).  exp(x - rowmax) / rowsum, true division. */
+int pglb_edge_softmax_csr_ws(int64_t num_edges, size_t *ws_bytes);
+int pglb_edge_softmax_csr_f32(const int64_t *indptr, const int64_t *eid, const float *logits,
+                              float *out, int64_t n_rows, int64_t num_edges, int64_t H,
+                              void *ws, size_t ws_bytes, void *stream);
+
+/* norm[i] = clip(float(degree[i]), 1)^-0.5 ; GF.degree_norm (graph_op.py:46-55) */
+int pglb_degree_norm_f32(const int64_t *degree, int64_t n, float *norm, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Host: METIS K-way behind the same call shape as graph_kernel.metis_partition
+ * (pgl/graph_kernel.pyx:434-472 <- pgl/partition.py:83-90).  libmetis (IDXTYPEWIDTH 64) is
+ * dlopen()ed from `libmetis_path` (NULL = default search); returns PGLB_ENOLIB if absent.
+ * ---------------------------------------------------------------------------------- */
+int pglb_metis_partition(const char *libmetis_path, int64_t num_nodes, const int64_t *indptr,
+                         const int64_t *adjncy, int64_t nparts, const int64_t *node_weights,
+                         const int64_t *edge_weights, int recursive, int64_t *part);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGLB_H_ */

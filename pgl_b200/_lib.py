@@ -1,0 +1,72 @@
+"""ctypes binding of libpglb.so (include/pglb.h).  The product path has no fallback: if the
+shared library is missing this module raises at import time."""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpglb.so")
+METIS_PATH = os.path.join(_HERE, "third_party", "libmetis_i64.so")
+
+PGLB_OK = 0
+PGLB_CUDA_ERR_BASE = 1000
+REDUCE = {"sum": 0, "mean": 1, "max": 2, "min": 3}
+MSG = {"copy": 0, "add": 1, "sub": 2, "mul": 3, "div": 4}
+BCAST_FULL, BCAST_HEAD, BCAST_SCALAR = 0, 1, 2
+
+
+class PglbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libpglb error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "pgl_b200: %s not found. Build it first with `python -m pgl_b200.build` "
+            "(or __graft_entry__.build()); there is no CPU / eager fallback." % LIB_PATH)
+    return ctypes.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+_p = c_void_p
+_i64 = c_int64
+
+_SIGS = {
+    "pglb_version": (c_int, []),
+    "pglb_last_error": (c_char_p, []),
+    "pglb_launch_count": (c_int64, []),
+    "pglb_csr_build_ws": (c_int, [_i64, _i64, POINTER(c_size_t)]),
+    "pglb_csr_build": (c_int, [_p, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _p, c_size_t, _p]),
+    "pglb_build_index_host": (c_int, [_p, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
+    "pglb_segment_ids_ws": (c_int, [_i64, POINTER(c_size_t)]),
+    "pglb_segment_ids": (c_int, [_p, _i64, _i64, _p, _p, _p, _p, c_size_t, _p]),
+    "pglb_segment_indptr": (c_int, [_p, _i64, _i64, _p, _p]),
+    "pglb_spmm_csr_ws": (c_int, [_i64, _i64, _i64, POINTER(c_size_t)]),
+    "pglb_spmm_csr_f32": (c_int, [_p, _p, _p, _p, _i64, _p, _i64, c_int, _p, _i64, _i64, _i64, _i64,
+                                  _i64, _i64, c_int, c_int, _p, _p, _i64, _p, c_size_t, _p]),
+    "pglb_send_uv_f32": (c_int, [_p, _p, _p, _i64, _p, _i64, _i64, _i64, c_int, _p, _p]),
+    "pglb_gather_rows_f32": (c_int, [_p, _i64, _p, _i64, _i64, _i64, _p, _i64, _p]),
+    "pglb_scatter_rows_f32": (c_int, [_p, _i64, _p, _i64, _i64, _p, _i64, _p]),
+    "pglb_edge_softmax_csr_ws": (c_int, [_i64, POINTER(c_size_t)]),
+    "pglb_edge_softmax_csr_f32": (c_int, [_p, _p, _p, _p, _i64, _i64, _i64, _p, c_size_t, _p]),
+    "pglb_degree_norm_f32": (c_int, [_p, _i64, _p, _p]),
+    "pglb_metis_partition": (c_int, [c_char_p, _i64, _p, _p, _i64, _p, _p, c_int, _p]),
+}
+
+for _name, (_res, _args) in _SIGS.items():
+    _f = getattr(lib, _name)
+    _f.restype = _res
+    _f.argtypes = _args
+
+
+def check(rc):
+    if rc != PGLB_OK:
+        msg = lib.pglb_last_error()
+        raise PglbError(rc, msg.decode("utf-8", "replace") if msg else "")
+
+
+def launch_count():
+    return int(lib.pglb_launch_count())

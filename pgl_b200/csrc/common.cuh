@@ -1,0 +1,58 @@
+// common.cuh -- shared helpers for libpglb (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "pglb.h"
+
+namespace pglb {
+
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+int fail(int code, const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define PGLB_CHECK_ARG(cond, code, ...)                  \
+    do {                                                 \
+        if (!(cond)) return ::pglb::fail(code, __VA_ARGS__); \
+    } while (0)
+
+#define PGLB_CUDA(call)                                             \
+    do {                                                            \
+        cudaError_t _e = (call);                                    \
+        if (_e != cudaSuccess) return ::pglb::cuda_fail(_e, #call); \
+    } while (0)
+
+#define PGLB_LAUNCH_CHECK(name)                                     \
+    do {                                                            \
+        ::pglb::count_launch();                                     \
+        cudaError_t _e = cudaGetLastError();                        \
+        if (_e != cudaSuccess) return ::pglb::cuda_fail(_e, name);  \
+    } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// ---- device helpers -------------------------------------------------------------------
+
+// streaming (evict-first) loads for index data that is read exactly once
+__device__ __forceinline__ int64_t ld_stream(const int64_t *p) { return __ldcs((const long long *)p); }
+__device__ __forceinline__ int64_t ld_ro(const int64_t *p) { return __ldg((const long long *)p); }
+
+}  // namespace pglb

@@ -1,0 +1,298 @@
+// edge_ops.cu -- edge-parallel and small per-row kernels of the send/recv path:
+// send_uv (K3), gather/scatter rows (K6/K7), fused per-row edge softmax (K5), degree_norm.
+#include "common.cuh"
+
+namespace pglb {
+
+constexpr int64_t SM_HUB_T = 2048;  // rows longer than this use one CTA instead of one warp
+
+__device__ __forceinline__ float msg_apply(int op, float a, float b) {
+    switch (op) {
+        case PGLB_MSG_ADD: return __fadd_rn(a, b);
+        case PGLB_MSG_SUB: return __fsub_rn(a, b);
+        case PGLB_MSG_MUL: return __fmul_rn(a, b);
+        case PGLB_MSG_DIV: return __fdiv_rn(a, b);
+        default: return a;
+    }
+}
+
+// ---- send_uv : out[e,:] = x[src[e],:] op y[dst[e],:] ----------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) send_uv_kernel(const float *__restrict__ x,
+                                                      const float *__restrict__ y,
+                                                      const int64_t *__restrict__ src, int64_t ss,
+                                                      const int64_t *__restrict__ dst, int64_t ds,
+                                                      int64_t E, int D, int op,
+                                                      float *__restrict__ out) {
+    const int dv = D / VEC;
+    const int64_t total = E * dv;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i / dv;
+        const int c = (int)(i - e * dv) * VEC;
+        const int64_t s = __ldg((const long long *)src + e * ss);
+        const int64_t d = __ldg((const long long *)dst + e * ds);
+        if (VEC == 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(x + s * D + c));
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(y + d * D + c));
+            float4 r;
+            r.x = msg_apply(op, a.x, b.x);
+            r.y = msg_apply(op, a.y, b.y);
+            r.z = msg_apply(op, a.z, b.z);
+            r.w = msg_apply(op, a.w, b.w);
+            __stcs(reinterpret_cast<float4 *>(out + e * D + c), r);
+        } else {
+            out[e * D + c] = msg_apply(op, __ldg(x + s * D + c), __ldg(y + d * D + c));
+        }
+    }
+}
+
+// ---- gather / scatter rows -------------------------------------------------------------
+template <int VEC, bool SCATTER>
+__global__ void __launch_bounds__(256) move_rows_kernel(const float *__restrict__ x, int64_t ldx,
+                                                        const int64_t *__restrict__ index,
+                                                        int64_t istride, int64_t n, int D,
+                                                        float *__restrict__ out, int64_t ldo) {
+    const int dv = D / VEC;
+    const int64_t total = n * dv;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / dv;
+        const int c = (int)(i - r * dv) * VEC;
+        const int64_t k = __ldg((const long long *)index + r * istride);
+        const int64_t rs = SCATTER ? r : k;
+        const int64_t rd = SCATTER ? k : r;
+        if (VEC == 4) {
+            *reinterpret_cast<float4 *>(out + rd * ldo + c) =
+                __ldg(reinterpret_cast<const float4 *>(x + rs * ldx + c));
+        } else {
+            out[rd * ldo + c] = __ldg(x + rs * ldx + c);
+        }
+    }
+}
+
+// ---- fused edge softmax over CSR rows --------------------------------------------------
+// A cooperative group of NT threads (a warp, or a whole CTA for long rows) owns one row.
+// Thread t handles head (t % HP) of slots (t / HP), (t / HP) + NT/HP, ...
+template <int NT>
+__device__ __forceinline__ float group_reduce(float v, bool is_max, int hp, float *smem) {
+    // reduce over threads with equal (t % hp); result valid in every thread
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        if (o >= hp) {
+            const float t = __shfl_xor_sync(0xffffffffu, v, o);
+            v = is_max ? fmaxf(v, t) : (v + t);
+        }
+    }
+    if (NT > 32) {
+        // now lanes 0..hp-1 of each warp hold the warp's value for head = lane
+        const int wid = threadIdx.x >> 5;
+        __syncthreads();
+        if (lane < hp) smem[wid * 32 + lane] = v;
+        __syncthreads();
+        float r = smem[lane % hp];
+        for (int w = 1; w < NT / 32; ++w) {
+            const float t = smem[w * 32 + (lane % hp)];
+            r = is_max ? fmaxf(r, t) : (r + t);
+        }
+        v = r;
+    }
+    return v;
+}
+
+template <int NT>
+__device__ __forceinline__ void softmax_row(const int64_t *__restrict__ eid,
+                                            const float *__restrict__ logits,
+                                            float *__restrict__ out, int64_t b, int64_t e, int H,
+                                            int h0, int hp, float *smem) {
+    const int t = (NT == 32) ? (threadIdx.x & 31) : threadIdx.x;
+    const int head = h0 + (t % hp);
+    const int srow = t / hp;
+    const int sstep = NT / hp;
+    const bool hact = head < H;
+    float m = -INFINITY;
+    for (int64_t j = b + srow; j < e; j += sstep) {
+        const int64_t id = eid ? __ldg((const long long *)eid + j) : j;
+        if (hact) m = fmaxf(m, __ldg(logits + id * H + head));
+    }
+    m = group_reduce<NT>(m, true, hp, smem);
+    float s = 0.0f;
+    for (int64_t j = b + srow; j < e; j += sstep) {
+        const int64_t id = eid ? __ldg((const long long *)eid + j) : j;
+        if (hact) s += expf(__ldg(logits + id * H + head) - m);
+    }
+    s = group_reduce<NT>(s, false, hp, smem);
+    for (int64_t j = b + srow; j < e; j += sstep) {
+        const int64_t id = eid ? __ldg((const long long *)eid + j) : j;
+        if (hact) out[id * H + head] = __fdiv_rn(expf(__ldg(logits + id * H + head) - m), s);
+    }
+}
+
+__global__ void __launch_bounds__(256) edge_softmax_warp_kernel(
+    const int64_t *__restrict__ indptr, const int64_t *__restrict__ eid,
+    const float *__restrict__ logits, float *__restrict__ out, int64_t n_rows, int H, int hp,
+    unsigned long long *hub_count, int64_t *hub_rows) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int h0 = blockIdx.y * hp;
+    for (int64_t r = warp; r < n_rows; r += nwarps) {
+        const int64_t b = ld_ro(indptr + r), e = ld_ro(indptr + r + 1);
+        if (e == b) continue;
+        if (e - b > SM_HUB_T) {
+            if ((threadIdx.x & 31) == 0 && blockIdx.y == 0) {
+                unsigned long long s = atomicAdd(hub_count, 1ull);
+                hub_rows[s] = r;
+            }
+            continue;
+        }
+        softmax_row<32>(eid, logits, out, b, e, H, h0, hp, nullptr);
+    }
+}
+
+__global__ void __launch_bounds__(256) edge_softmax_hub_kernel(
+    const int64_t *__restrict__ indptr, const int64_t *__restrict__ eid,
+    const float *__restrict__ logits, float *__restrict__ out, int H, int hp,
+    const unsigned long long *hub_count, const int64_t *hub_rows) {
+    __shared__ float smem[8 * 32];
+    const int64_t n = (int64_t)*hub_count;
+    const int h0 = blockIdx.y * hp;
+    for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const int64_t r = hub_rows[i];
+        softmax_row<256>(eid, logits, out, indptr[r], indptr[r + 1], H, h0, hp, smem);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) degree_norm_kernel(const int64_t *__restrict__ degree,
+                                                          int64_t n, float *__restrict__ norm) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float d = (float)degree[i];
+        d = fmaxf(d, 1.0f);
+        norm[i] = __fdiv_rn(1.0f, __fsqrt_rn(d));
+    }
+}
+
+static inline bool a16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline int grid_for(int64_t total) {
+    int64_t b = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 32;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace pglb
+
+using namespace pglb;
+
+extern "C" int pglb_send_uv_f32(const float *x, const float *y, const int64_t *src,
+                                int64_t src_stride, const int64_t *dst, int64_t dst_stride,
+                                int64_t E, int64_t D, int msg_op, float *out, void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    PGLB_CHECK_ARG(E >= 0 && D >= 0 && D <= INT32_MAX, PGLB_EINVAL, "pglb_send_uv_f32: bad size");
+    PGLB_CHECK_ARG(msg_op >= PGLB_MSG_ADD && msg_op <= PGLB_MSG_DIV, PGLB_EINVAL,
+                   "pglb_send_uv_f32: unknown msg_op %d", msg_op);
+    if (E == 0 || D == 0) return PGLB_OK;
+    PGLB_CHECK_ARG(x && y && src && dst && out, PGLB_EINVAL, "pglb_send_uv_f32: NULL pointer");
+    PGLB_CHECK_ARG(src_stride >= 1 && dst_stride >= 1, PGLB_EINVAL, "pglb_send_uv_f32: bad stride");
+    if (D % 4 == 0 && a16(x) && a16(y) && a16(out)) {
+        send_uv_kernel<4><<<grid_for(E * (D / 4)), 256, 0, stream>>>(
+            x, y, src, src_stride, dst, dst_stride, E, (int)D, msg_op, out);
+    } else {
+        send_uv_kernel<1><<<grid_for(E * D), 256, 0, stream>>>(x, y, src, src_stride, dst,
+                                                                dst_stride, E, (int)D, msg_op, out);
+    }
+    PGLB_LAUNCH_CHECK("send_uv_kernel");
+    return PGLB_OK;
+}
+
+extern "C" int pglb_gather_rows_f32(const float *x, int64_t ldx, const int64_t *index,
+                                    int64_t index_stride, int64_t n, int64_t D, float *out,
+                                    int64_t ldo, void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    PGLB_CHECK_ARG(n >= 0 && D >= 0 && D <= INT32_MAX, PGLB_EINVAL, "pglb_gather_rows_f32: bad size");
+    if (n == 0 || D == 0) return PGLB_OK;
+    PGLB_CHECK_ARG(x && index && out, PGLB_EINVAL, "pglb_gather_rows_f32: NULL pointer");
+    PGLB_CHECK_ARG(ldx >= D && ldo >= D && index_stride >= 1, PGLB_ESHAPE,
+                   "pglb_gather_rows_f32: bad leading dimension / stride");
+    if (D % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && a16(x) && a16(out))
+        move_rows_kernel<4, false><<<grid_for(n * (D / 4)), 256, 0, stream>>>(
+            x, ldx, index, index_stride, n, (int)D, out, ldo);
+    else
+        move_rows_kernel<1, false><<<grid_for(n * D), 256, 0, stream>>>(x, ldx, index, index_stride,
+                                                                        n, (int)D, out, ldo);
+    PGLB_LAUNCH_CHECK("gather_rows_kernel");
+    return PGLB_OK;
+}
+
+extern "C" int pglb_scatter_rows_f32(const float *x, int64_t ldx, const int64_t *index, int64_t n,
+                                     int64_t D, float *out, int64_t ldo, void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    PGLB_CHECK_ARG(n >= 0 && D >= 0 && D <= INT32_MAX, PGLB_EINVAL, "pglb_scatter_rows_f32: bad size");
+    if (n == 0 || D == 0) return PGLB_OK;
+    PGLB_CHECK_ARG(x && index && out, PGLB_EINVAL, "pglb_scatter_rows_f32: NULL pointer");
+    PGLB_CHECK_ARG(ldx >= D && ldo >= D, PGLB_ESHAPE, "pglb_scatter_rows_f32: bad leading dimension");
+    if (D % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && a16(x) && a16(out))
+        move_rows_kernel<4, true><<<grid_for(n * (D / 4)), 256, 0, stream>>>(x, ldx, index, 1, n,
+                                                                             (int)D, out, ldo);
+    else
+        move_rows_kernel<1, true><<<grid_for(n * D), 256, 0, stream>>>(x, ldx, index, 1, n, (int)D,
+                                                                       out, ldo);
+    PGLB_LAUNCH_CHECK("scatter_rows_kernel");
+    return PGLB_OK;
+}
+
+extern "C" int pglb_edge_softmax_csr_ws(int64_t num_edges, size_t *ws_bytes) {
+    PGLB_CHECK_ARG(ws_bytes != nullptr && num_edges >= 0, PGLB_EINVAL,
+                   "pglb_edge_softmax_csr_ws: bad args");
+    *ws_bytes = 256 + sizeof(int64_t) * (size_t)(num_edges / (SM_HUB_T + 1) + 1);
+    return PGLB_OK;
+}
+
+extern "C" int pglb_edge_softmax_csr_f32(const int64_t *indptr, const int64_t *eid,
+                                         const float *logits, float *out, int64_t n_rows,
+                                         int64_t E, int64_t H, void *ws, size_t ws_bytes,
+                                         void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    PGLB_CHECK_ARG(n_rows >= 0 && E >= 0 && H >= 0 && H <= INT32_MAX, PGLB_EINVAL,
+                   "pglb_edge_softmax_csr_f32: bad size");
+    if (n_rows == 0 || E == 0 || H == 0) return PGLB_OK;
+    PGLB_CHECK_ARG(indptr && logits && out, PGLB_EINVAL, "pglb_edge_softmax_csr_f32: NULL pointer");
+    size_t need = 0;
+    pglb_edge_softmax_csr_ws(E, &need);
+    PGLB_CHECK_ARG(ws && ws_bytes >= need, PGLB_EWORKSPACE,
+                   "pglb_edge_softmax_csr_f32: workspace of %zu bytes needed (got %zu)", need,
+                   ws_bytes);
+    unsigned long long *hub_count = reinterpret_cast<unsigned long long *>(ws);
+    int64_t *hub_rows = reinterpret_cast<int64_t *>(reinterpret_cast<char *>(ws) + 256);
+    PGLB_CUDA(cudaMemsetAsync(hub_count, 0, 8, stream));
+    int hp = 1;
+    while (hp < H && hp < 32) hp <<= 1;
+    const int tiles = (int)((H + hp - 1) / hp);
+    int64_t blocks = (n_rows + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 64;
+    if (blocks > cap) blocks = cap;
+    dim3 grid((unsigned)blocks, (unsigned)tiles);
+    edge_softmax_warp_kernel<<<grid, 256, 0, stream>>>(indptr, eid, logits, out, n_rows, (int)H, hp,
+                                                       hub_count, hub_rows);
+    PGLB_LAUNCH_CHECK("edge_softmax_warp_kernel");
+    if (E > SM_HUB_T) {
+        dim3 hgrid((unsigned)(sm_count() * 4), (unsigned)tiles);
+        edge_softmax_hub_kernel<<<hgrid, 256, 0, stream>>>(indptr, eid, logits, out, (int)H, hp,
+                                                           hub_count, hub_rows);
+        PGLB_LAUNCH_CHECK("edge_softmax_hub_kernel");
+    }
+    return PGLB_OK;
+}
+
+extern "C" int pglb_degree_norm_f32(const int64_t *degree, int64_t n, float *norm, void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    PGLB_CHECK_ARG(n >= 0, PGLB_EINVAL, "pglb_degree_norm_f32: bad size");
+    if (n == 0) return PGLB_OK;
+    PGLB_CHECK_ARG(degree && norm, PGLB_EINVAL, "pglb_degree_norm_f32: NULL pointer");
+    degree_norm_kernel<<<grid_for(n), 256, 0, stream>>>(degree, n, norm);
+    PGLB_LAUNCH_CHECK("degree_norm_kernel");
+    return PGLB_OK;
+}

@@ -1,0 +1,356 @@
+"""Torch-tensor front end of the C-ABI (include/pglb.h): allocates outputs / workspaces with
+torch, passes raw device pointers + the current CUDA stream to libpglb.  CUDA tensors only --
+every function raises on CPU tensors; there is no eager / CPU fallback on this path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import BCAST_FULL, BCAST_HEAD, BCAST_SCALAR, MSG, REDUCE, check, lib
+
+_ws_cache = {}
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "pgl_b200: tensor-mode ops run on CUDA tensors only (got a %s tensor); "
+                "there is no CPU fallback on the send/recv path" % t.device)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def workspace(device, nbytes):
+    """Per-(device, stream) scratch buffer, grown geometrically; stream-ordered reuse."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        n = max(int(nbytes), 1 << 20)
+        if buf is not None:
+            n = max(n, int(buf.numel() * 1.5))
+        buf = torch.empty(n, dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _i64(t):
+    if t.dtype != torch.int64:
+        t = t.to(torch.int64)
+    return t
+
+
+def _f32_2d(t):
+    """[n, d1, d2, ...] -> contiguous [n, D] float32 view (no copy when already so)."""
+    if t.dtype != torch.float32:
+        raise TypeError("pgl_b200: float32 features expected on the CUDA path, got %s" % t.dtype)
+    t2 = t.reshape(t.shape[0], -1) if t.dim() != 2 else t
+    if not t2.is_contiguous():
+        t2 = t2.contiguous()
+    return t2
+
+
+# ------------------------------------------------------------------------------------------
+# index construction
+# ------------------------------------------------------------------------------------------
+
+
+def csr_build(u, v, num_nodes):
+    """Device twin of graph_kernel.build_index (reference pgl/graph_kernel.pyx:59-88).
+    u, v: 1-D int64 CUDA tensors (strided views such as edges[:, 1] are read in place).
+    Returns (degree, sorted_v, sorted_u, sorted_eid, indptr) like the reference."""
+    require_cuda(u, v)
+    u = _i64(u)
+    v = _i64(v)
+    E = int(u.shape[0])
+    N = int(num_nodes)
+    dev = u.device
+    degree = torch.empty(N, dtype=torch.int64, device=dev)
+    indptr = torch.empty(N + 1, dtype=torch.int64, device=dev)
+    su = torch.empty(E, dtype=torch.int64, device=dev)
+    sv = torch.empty(E, dtype=torch.int64, device=dev)
+    se = torch.empty(E, dtype=torch.int64, device=dev)
+    need = ctypes.c_size_t(0)
+    check(lib.pglb_csr_build_ws(E, N, ctypes.byref(need)))
+    ws = workspace(dev, need.value)
+    us = u.stride(0) if E > 0 else 1
+    vs = v.stride(0) if E > 0 else 1
+    with torch.cuda.device(dev):
+        check(lib.pglb_csr_build(_ptr(u), max(us, 1), _ptr(v), max(vs, 1), E, N, _ptr(degree),
+                                 _ptr(indptr), _ptr(su), _ptr(sv), _ptr(se), _ptr(ws),
+                                 ws.numel(), _stream()))
+    return degree, sv, su, se, indptr
+
+
+def segment_ids_from_indptr(indptr, num_edges):
+    """(uniq_ind, segment_ids) of a CSR == paddle.unique(sorted_key, return_inverse=True)
+    (reference pgl/utils/helper.py:156-160).  One D2H read of K (the reference's unique syncs too)."""
+    require_cuda(indptr)
+    N = int(indptr.shape[0]) - 1
+    E = int(num_edges)
+    dev = indptr.device
+    uniq = torch.empty(max(N, 0), dtype=torch.int64, device=dev)
+    seg = torch.empty(E, dtype=torch.int64, device=dev)
+    k = torch.zeros(1, dtype=torch.int64, device=dev)
+    need = ctypes.c_size_t(0)
+    check(lib.pglb_segment_ids_ws(N, ctypes.byref(need)))
+    ws = workspace(dev, need.value)
+    with torch.cuda.device(dev):
+        check(lib.pglb_segment_ids(_ptr(indptr), N, E, _ptr(uniq), _ptr(seg), _ptr(k), _ptr(ws),
+                                   ws.numel(), _stream()))
+    return uniq[: int(k.item())], seg
+
+
+def segment_indptr(segment_ids, num_segments):
+    require_cuda(segment_ids)
+    ids = _i64(segment_ids).contiguous()
+    E = int(ids.shape[0])
+    K = int(num_segments)
+    indptr = torch.empty(K + 1, dtype=torch.int64, device=ids.device)
+    with torch.cuda.device(ids.device):
+        check(lib.pglb_segment_indptr(_ptr(ids), E, K, _ptr(indptr), _stream()))
+    return indptr
+
+
+# ------------------------------------------------------------------------------------------
+# aggregation
+# ------------------------------------------------------------------------------------------
+
+
+def _spmm_raw(indptr, cols, x2, n_dst, reduce_op, eid=None, y2=None, y_bcast=BCAST_FULL,
+              head_dim=1, msg_op="copy", scale_src=None, scale_dst=None, max_degree=-1,
+              num_edges=None, out=None):
+    dev = x2.device
+    D = int(x2.shape[1])
+    E = int(num_edges if num_edges is not None else (cols.shape[0] if cols is not None else 0))
+    if out is None:
+        out = torch.empty((n_dst, D), dtype=torch.float32, device=dev)
+    ws = None
+    wsn = 0
+    if not (0 <= max_degree <= 1024) and E > 1024:
+        need = ctypes.c_size_t(0)
+        check(lib.pglb_spmm_csr_ws(n_dst, E, D, ctypes.byref(need)))
+        ws = workspace(dev, need.value)
+        wsn = ws.numel()
+    with torch.cuda.device(dev):
+        check(lib.pglb_spmm_csr_f32(
+            _ptr(indptr), _ptr(cols), _ptr(eid), _ptr(x2), x2.stride(0), _ptr(y2),
+            (y2.stride(0) if y2 is not None else 0), y_bcast, _ptr(out), out.stride(0), n_dst,
+            int(x2.shape[0]), E, D, head_dim, MSG[msg_op], REDUCE[reduce_op], _ptr(scale_src),
+            _ptr(scale_dst), int(max_degree), _ptr(ws), wsn, _stream()))
+    return out
+
+
+class _CopyAgg(torch.autograd.Function):
+    """out[d] = reduce_{e -> d} scale_src[src] * x[src]  (* scale_dst[d]); sum / mean.
+    Backward is the same kernel on the reverse (src-keyed) CSR."""
+
+    @staticmethod
+    def forward(ctx, x2, fwd, bwd, n_dst, reduce_op, scale_src, scale_dst):
+        ctx.bwd = bwd
+        ctx.reduce_op = reduce_op
+        ctx.n_src = int(x2.shape[0])
+        ctx.scales = (scale_src, scale_dst)
+        ctx.fwd = fwd
+        return _spmm_raw(fwd["indptr"], fwd["cols"], x2, n_dst, reduce_op, scale_src=scale_src,
+                         scale_dst=scale_dst, max_degree=fwd.get("max_degree", -1))
+
+    @staticmethod
+    def backward(ctx, g):
+        bwd = ctx.bwd() if callable(ctx.bwd) else ctx.bwd
+        if bwd is None:
+            raise RuntimeError("pgl_b200: backward of this aggregation needs the reverse CSR")
+        g = g.contiguous()
+        scale_src, scale_dst = ctx.scales
+        s_in = scale_dst
+        if ctx.reduce_op == "mean":
+            inv = 1.0 / torch.clamp(ctx.fwd["degree"].to(torch.float32), min=1.0)
+            s_in = inv if s_in is None else s_in * inv
+        gx = _spmm_raw(bwd["indptr"], bwd["cols"], g, ctx.n_src, "sum", scale_src=s_in,
+                       scale_dst=scale_src, max_degree=bwd.get("max_degree", -1))
+        return gx, None, None, None, None, None, None
+
+
+def aggregate_copy(x, fwd, n_dst, reduce_op="sum", bwd=None, scale_src=None, scale_dst=None):
+    """send_u_recv on a cached dst-CSR.  fwd/bwd: dicts {indptr, cols, degree, max_degree}."""
+    require_cuda(x)
+    shape = x.shape
+    x2 = _f32_2d(x)
+    if reduce_op in ("sum", "mean") and x2.requires_grad and torch.is_grad_enabled():
+        out = _CopyAgg.apply(x2, fwd, bwd, n_dst, reduce_op, scale_src, scale_dst)
+    else:
+        out = _spmm_raw(fwd["indptr"], fwd["cols"], x2.detach() if reduce_op in ("sum", "mean") else x2,
+                        n_dst, reduce_op, scale_src=scale_src, scale_dst=scale_dst,
+                        max_degree=fwd.get("max_degree", -1))
+    return out.reshape((n_dst,) + tuple(shape[1:]))
+
+
+def classify_bcast(x_shape, y_shape):
+    """Map (x feature dims, y feature dims) to a kernel broadcast mode.
+    Returns (mode, head_dim) or None when y must be materialised by expand()."""
+    xf = tuple(x_shape[1:])
+    yf = tuple(y_shape[1:])
+    D = 1
+    for s in xf:
+        D *= s
+    ny = 1
+    for s in yf:
+        ny *= s
+    if ny == 1:
+        return BCAST_SCALAR, 1
+    if len(yf) < len(xf):
+        yf = (1,) * (len(xf) - len(yf)) + yf
+    if len(yf) != len(xf):
+        return None
+    if yf == xf:
+        return BCAST_FULL, 1
+    # [.., H, 1, 1] against [.., H, a, b]: leading dims equal, trailing dims of y all 1
+    k = len(xf)
+    while k > 0 and yf[k - 1] == 1:
+        k -= 1
+    if yf[:k] == xf[:k]:
+        hd = 1
+        for s in xf[k:]:
+            hd *= s
+        return BCAST_HEAD, hd
+    return None
+
+
+def aggregate_ue(x, y, fwd, n_dst, message_op="add", reduce_op="sum"):
+    """send_ue_recv on a cached dst-CSR: y is in original edge order, read through eid."""
+    require_cuda(x, y)
+    xs = tuple(x.shape)
+    if y.dim() == 1:
+        y = y.reshape(-1, 1)
+    out_feat = torch.broadcast_shapes(tuple(x.shape[1:]) if x.dim() > 1 else (1,), tuple(y.shape[1:]))
+    if tuple(out_feat) != tuple(xs[1:]):
+        x = x.reshape((xs[0],) + (1,) * (len(out_feat) - len(xs[1:])) + tuple(xs[1:]))
+        x = x.expand((xs[0],) + tuple(out_feat)).contiguous()
+    cls = classify_bcast(x.shape, y.shape)
+    if cls is None:
+        y = y.expand((y.shape[0],) + tuple(out_feat)).contiguous()
+        cls = (BCAST_FULL, 1)
+    mode, hd = cls
+    x2 = _f32_2d(x)
+    y2 = _f32_2d(y)
+    out = _spmm_raw(fwd["indptr"], fwd["cols"], x2, n_dst, reduce_op, eid=fwd["eid"], y2=y2,
+                    y_bcast=mode, head_dim=hd, msg_op=message_op,
+                    max_degree=fwd.get("max_degree", -1))
+    return out.reshape((n_dst,) + tuple(out_feat))
+
+
+def segment_reduce(data, segment_ids, pool_type, num_segments=None, indptr=None, cols=None,
+                   max_degree=-1):
+    """paddle.geometric.segment_* over sorted ids (reference pgl/math.py:36-42).
+    `cols` (optional) fuses a row gather: slot j reads data[cols[j]] (lazy messages)."""
+    require_cuda(data)
+    d2 = _f32_2d(data)
+    if indptr is None:
+        ids = _i64(segment_ids)
+        E = int(ids.shape[0])
+        if num_segments is None:
+            num_segments = int(ids[-1].item()) + 1 if E > 0 else 0
+        indptr = segment_indptr(ids, num_segments)
+    else:
+        E = int(cols.shape[0]) if cols is not None else int(d2.shape[0])
+        num_segments = int(indptr.shape[0]) - 1
+    out = _spmm_raw(indptr, cols, d2, int(num_segments), pool_type, num_edges=E,
+                    max_degree=max_degree)
+    return out.reshape((int(num_segments),) + tuple(data.shape[1:]))
+
+
+# ------------------------------------------------------------------------------------------
+# edge-parallel
+# ------------------------------------------------------------------------------------------
+
+
+def send_uv(x, y, src, dst, message_op="add"):
+    require_cuda(x, y, src, dst)
+    xf = tuple(x.shape[1:]) if x.dim() > 1 else (1,)
+    yf = tuple(y.shape[1:]) if y.dim() > 1 else (1,)
+    of = tuple(torch.broadcast_shapes(xf, yf))
+    if xf != of:
+        x = x.reshape((x.shape[0],) + (1,) * (len(of) - len(xf)) + xf).expand((x.shape[0],) + of)
+    if yf != of:
+        y = y.reshape((y.shape[0],) + (1,) * (len(of) - len(yf)) + yf).expand((y.shape[0],) + of)
+    x2 = _f32_2d(x.reshape(x.shape[0], -1) if x.dim() != 2 else x)
+    y2 = _f32_2d(y.reshape(y.shape[0], -1) if y.dim() != 2 else y)
+    E = int(src.shape[0])
+    D = int(x2.shape[1])
+    out = torch.empty((E, D), dtype=torch.float32, device=x2.device)
+    with torch.cuda.device(x2.device):
+        check(lib.pglb_send_uv_f32(_ptr(x2), _ptr(y2), _ptr(src), max(src.stride(0), 1) if E else 1,
+                                   _ptr(dst), max(dst.stride(0), 1) if E else 1, E, D,
+                                   MSG[message_op], _ptr(out), _stream()))
+    return out.reshape((E,) + of)
+
+
+def gather_rows(x, index):
+    """paddle.gather(x, index, axis=0)."""
+    require_cuda(x, index)
+    index = _i64(index)
+    n = int(index.shape[0])
+    if x.dtype != torch.float32:
+        return x.index_select(0, index.contiguous())  # integer gathers (degree subsets): torch device op
+    x2 = _f32_2d(x)
+    D = int(x2.shape[1])
+    out = torch.empty((n, D), dtype=torch.float32, device=x2.device)
+    with torch.cuda.device(x2.device):
+        check(lib.pglb_gather_rows_f32(_ptr(x2), x2.stride(0), _ptr(index),
+                                       max(index.stride(0), 1) if n else 1, n, D, _ptr(out),
+                                       out.stride(0), _stream()))
+    return out.reshape((n,) + tuple(x.shape[1:]))
+
+
+def scatter_rows(init, index, updates):
+    """paddle.scatter(init, index, updates, overwrite=True) for unique indices (out-of-place)."""
+    require_cuda(init, index, updates)
+    out = init.clone()
+    o2 = out.reshape(out.shape[0], -1) if out.dim() != 2 else out
+    u2 = _f32_2d(updates)
+    index = _i64(index).contiguous()
+    n = int(index.shape[0])
+    with torch.cuda.device(out.device):
+        check(lib.pglb_scatter_rows_f32(_ptr(u2), u2.stride(0), _ptr(index), n, int(u2.shape[1]),
+                                        _ptr(o2), o2.stride(0), _stream()))
+    return out
+
+
+def edge_softmax_csr(indptr, eid, logits, num_edges):
+    """Fused per-row softmax; eid=None -> rows are contiguous slots (segment_softmax)."""
+    require_cuda(indptr, logits)
+    shape = logits.shape
+    l2 = logits.reshape(shape[0], -1) if logits.dim() != 2 else logits
+    l2 = _f32_2d(l2)
+    H = int(l2.shape[1])
+    E = int(num_edges)
+    out = torch.empty_like(l2)
+    need = ctypes.c_size_t(0)
+    check(lib.pglb_edge_softmax_csr_ws(E, ctypes.byref(need)))
+    ws = workspace(l2.device, need.value)
+    with torch.cuda.device(l2.device):
+        check(lib.pglb_edge_softmax_csr_f32(_ptr(indptr), _ptr(eid), _ptr(l2), _ptr(out),
+                                            int(indptr.shape[0]) - 1, E, H, _ptr(ws), ws.numel(),
+                                            _stream()))
+    return out.reshape(shape)
+
+
+def degree_norm(degree):
+    require_cuda(degree)
+    degree = _i64(degree).contiguous()
+    n = int(degree.shape[0])
+    out = torch.empty(n, dtype=torch.float32, device=degree.device)
+    with torch.cuda.device(degree.device):
+        check(lib.pglb_degree_norm_f32(_ptr(degree), n, _ptr(out), _stream()))
+    return out.reshape(-1, 1)
+
+
+def launch_count():
+    return _lib.launch_count()

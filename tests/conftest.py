@@ -1,0 +1,37 @@
+import os
+import shutil
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # build the native pieces once (no-ops when up to date; nvcc cross-compiles without a GPU)
+    if shutil.which("nvcc"):
+        from pgl_b200 import build as pbuild
+        pbuild.build_all()
+    from oracle import build as obuild
+    obuild.build_oracle_c()
+    if os.path.isdir("/root/reference"):
+        obuild.build_ref()
+
+
+@pytest.fixture(scope="session")
+def kat():
+    import json
+    with open(os.path.join(GOLDEN, "kat.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def oracle_c():
+    import ctypes
+    from oracle import build as obuild
+    return ctypes.CDLL(obuild.build_oracle_c())
