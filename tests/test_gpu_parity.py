@@ -1,0 +1,519 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the oracle on the same seeded
+inputs, against the reference's known-answer tests, and the reference-generated goldens.
+
+Bars: bit-exact for integer/index work and for the reference's exact-equality KATs;
+fp32 reductions: bit-exact against the sequential restatement for rows below the hub
+threshold (same summation order), <= 1e-4 relative otherwise.
+"""
+import os
+from fractions import Fraction
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RTOL = 1e-4
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12) if a.size else 0.0
+
+
+@pytest.fixture(scope="module")
+def pgl():
+    import pgl_b200
+    return pgl_b200
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def make_graph(pgl, edges, n, **kw):
+    g = pgl.Graph(edges=np.asarray(edges, np.int64), num_nodes=n, **kw)
+    g.tensor()
+    return g
+
+
+# ---------------------------------------------------------------- integer side: bit-exact
+def test_csr_build_vs_reference_golden(pgl):
+    g = np.load(os.path.join(GOLDEN, "ref_build_index.npz"))
+    for name in ("tiny", "uniform", "powerlaw", "gaps"):
+        n = int(g[name + "_n"])
+        deg, sv, su, se, ip = pgl.ops.csr_build(dev(g[name + "_u"]), dev(g[name + "_v"]), n)
+        assert (deg.cpu().numpy() == g[name + "_degree"]).all(), name
+        assert (sv.cpu().numpy() == g[name + "_sorted_v"]).all(), name
+        assert (su.cpu().numpy() == g[name + "_sorted_u"]).all(), name
+        assert (se.cpu().numpy() == g[name + "_sorted_eid"]).all(), name
+        assert (ip.cpu().numpy() == g[name + "_indptr"]).all(), name
+
+
+def test_csr_build_random_vs_oracle(pgl):
+    for n, e, seed in ((1, 5, 0), (1000, 50000, 1), (200000, 2000000, 2)):
+        edges = O.chung_lu_edges(n, e, seed=seed)
+        ed = dev(edges)
+        # strided views of the [E,2] tensor are consumed in place
+        deg, sv, su, se, ip = pgl.ops.csr_build(ed[:, 1], ed[:, 0], n)
+        odeg, osv, osu, ose, oip = O.adj_dst_index(edges, n)
+        assert (deg.cpu().numpy() == odeg).all()
+        assert (ip.cpu().numpy() == oip).all()
+        assert (se.cpu().numpy() == ose).all()
+        assert (sv.cpu().numpy() == osv).all()
+        assert (su.cpu().numpy() == osu).all()
+
+
+def test_degree_and_segment_ids(pgl, kat):
+    k = kat["degree"]
+    g = make_graph(pgl, k["edges"], k["num_nodes"])
+    assert g.is_tensor()
+    assert g.indegree().cpu().tolist() == k["indegree"]
+    assert g.outdegree().cpu().tolist() == k["outdegree"]
+    sub = torch.tensor(k["subset"]).cuda()
+    assert g.indegree(nodes=sub).cpu().tolist() == [k["indegree"][i] for i in k["subset"]]
+    assert g.outdegree(nodes=sub).cpu().tolist() == [k["outdegree"][i] for i in k["subset"]]
+    # segment ids == paddle.unique(sorted dst, return_inverse)
+    edges = O.chung_lu_edges(500, 3000, seed=9)
+    g = make_graph(pgl, edges, 500)
+    for by in ("dst", "src"):
+        s, d, eid = g.sorted_edges(by)
+        uniq, seg = g.get_segment_ids(s, d, segment_by=by)
+        os_, od_, oe_ = O.sorted_edges(edges, 500, by)
+        ou, oseg = O.unique_segment(od_ if by == "dst" else os_)
+        assert (eid.cpu().numpy() == oe_).all()
+        assert (uniq.cpu().numpy() == ou).all()
+        assert (seg.cpu().numpy() == oseg).all()
+    from pgl_b200.utils.helper import unique_segment
+    key = dev(np.sort(np.random.default_rng(1).integers(0, 50, 400)))
+    u2, s2 = unique_segment(key)
+    ou2, os2 = O.unique_segment(key.cpu().numpy())
+    assert (u2.cpu().numpy() == ou2).all() and (s2.cpu().numpy() == os2).all()
+
+
+# ---------------------------------------------------------------- reference KATs (exact)
+def test_kat_send_recv(pgl, kat):
+    k = kat["send_recv_sum"]
+    g = make_graph(pgl, k["edges"], k["num_nodes"],
+                   node_feat={"nfeat": np.array(k["nfeat"], np.float32)})
+    out = g.send_recv(g.node_feat["nfeat"], reduce_func="sum").cpu().numpy()
+    assert (out == np.array(k["ground"], np.float32)).all()
+
+
+def test_kat_send_and_recv_udf(pgl, kat):
+    k = kat["send_and_recv"]
+    g = make_graph(pgl, k["edges"], k["num_nodes"],
+                   node_feat={"nfeat": np.array(k["nfeat"], np.float32)})
+
+    def send_func1(src_feat, dst_feat, edge_feat):
+        return src_feat
+
+    def send_func2(src_feat, dst_feat, edge_feat):
+        return {"h": src_feat["h"]}
+
+    def reduce_func(msg):
+        return msg.reduce_sum(msg["h"])
+
+    for f in (send_func1, send_func2):
+        msg = g.send(f, src_feat={"h": g.node_feat["nfeat"]})
+        assert (msg["h"].cpu().numpy() == np.array(k["msg_ground"], np.float32)).all()
+        out = g.recv(reduce_func, msg).cpu().numpy()
+        assert (out == np.array(k["recv_ground"], np.float32)).all()
+    with pytest.raises(TypeError):
+        g.send(lambda s, d, e: s["h"], src_feat={"h": g.node_feat["nfeat"]})
+    with pytest.raises(TypeError):
+        g.recv(reduce_func, [1])
+    with pytest.raises(TypeError):
+        g.recv("sum", {})
+    with pytest.raises(ValueError):
+        g.send(send_func1, src_feat={"h": g.node_feat["nfeat"]}, node_feat={"h": g.node_feat["nfeat"]})
+    with pytest.raises(AssertionError):
+        g.send_recv(g.node_feat["nfeat"], "prod")
+    with pytest.raises(NotImplementedError):
+        g.send_ue(None, None)
+
+
+def test_kat_send_func(pgl, kat):
+    k = kat["send_func"]
+    g = make_graph(pgl, k["edges"], k["num_nodes"],
+                   node_feat={"nfeat": np.array(k["nfeat"], np.float32)},
+                   edge_feat={"efeat": np.array(k["efeat"], np.float32)})
+    both = lambda sf, df, ef: {"sh": sf["h"], "dh": df["h"], "e": ef["e"]}  # noqa: E731
+    msg = g.send(both, node_feat={"h": g.node_feat["nfeat"]}, edge_feat={"e": g.edge_feat["efeat"]})
+    assert (msg["sh"].cpu().numpy() == np.array(k["target_src"])).all()
+    assert (msg["dh"].cpu().numpy() == np.array(k["target_dst"])).all()
+    assert (msg["e"].cpu().numpy() == np.array(k["target_edge"])).all()
+
+
+def test_kat_segment_and_softmax(pgl, kat):
+    k = kat["segment_docstrings"]
+    d = dev(np.array(k["data"], np.float32))
+    s = dev(np.array(k["seg_ids"], np.int64))
+    s32 = dev(np.array(k["seg_ids"], np.int32))
+    for op_ in ("sum", "mean", "min", "max"):
+        want = np.array(k[op_], np.float32)
+        assert (getattr(pgl.math, "segment_" + op_)(d, s).cpu().numpy() == want).all()
+        assert (pgl.math.segment_pool(d, s32, op_).cpu().numpy() == want).all()
+    with pytest.raises(ValueError):
+        pgl.math.segment_pool(d, s, "prod")
+    for name in ("segment_softmax", "segment_softmax_overflow"):
+        kk = kat[name]
+        out = pgl.math.segment_softmax(dev(np.array(kk["data"], np.float32)),
+                                       dev(np.array(kk["seg_ids"], np.int64))).cpu().numpy()
+        assert not np.isnan(out).any()
+        np.testing.assert_allclose(out, np.array(kk["ground"], np.float32), atol=1e-6)
+
+
+def test_kat_edge_softmax_exact(pgl, kat):
+    k = kat["edge_softmax"]
+    g = make_graph(pgl, k["edges"], k["num_nodes"])
+    lg = dev(np.array(k["logits"], np.float32))
+    import pgl_b200.nn.functional as F
+    for by in ("dst", "src"):
+        res = np.array([float(Fraction(s)) for s in k[by]], dtype=np.float32)
+        out = F.edge_softmax(g, lg, norm_by=by).cpu().numpy()
+        assert (out == res).all(), (by, out, res)
+
+
+def test_kat_send_ue_recv_and_bigraph(pgl, kat):
+    k = kat["send_ue_recv_add_sum"]
+    g = make_graph(pgl, k["edges"], k["num_nodes"],
+                   node_feat={"nfeat": np.array(k["nfeat"], np.float32)},
+                   edge_feat={"efeat": np.array(k["efeat"], np.float32)})
+    out = g.send_ue_recv(g.node_feat["nfeat"], g.edge_feat["efeat"]).cpu().numpy()
+    assert (out == np.array(k["ground"], np.float32)).all()
+    # rectangular (5 src x 4 dst) through out_size
+    k = kat["bigraph_send_recv_sum"]
+    g = make_graph(pgl, k["edges"], k["src_num_nodes"])
+    out = g.send_recv(dev(np.array(k["src_nfeat"], np.float32)), "sum",
+                      out_size=k["dst_num_nodes"]).cpu().numpy()
+    assert (out == np.array(k["ground"], np.float32)).all()
+    # recv_mode="src"
+    k = kat["bigraph_recv_src"]
+    g = make_graph(pgl, k["edges"], k["src_num_nodes"])
+    dstf = np.zeros((k["src_num_nodes"], 4), np.float32)
+    dstf[: k["dst_num_nodes"]] = np.array(k["dst_nfeat"], np.float32)
+    msg = g.send(lambda s, d, e: d, dst_feat={"h": dev(dstf)})
+    assert (msg["h"].cpu().numpy() == np.array(k["dst_msg_ground"], np.float32)).all()
+    out = g.recv(lambda m: m.reduce_sum(m["h"]), msg, recv_mode="src").cpu().numpy()
+    assert (out == np.array(k["dst_recv"], np.float32)).all()
+
+
+def test_readme_toy_config1(pgl, kat):
+    k = kat["readme_toy"]
+    np.random.seed(k["seed"])
+    x = np.random.randn(k["num_nodes"], k["dim"]).astype(np.float32)
+    g = make_graph(pgl, k["edges"], k["num_nodes"], node_feat={"feature": x})
+    msg = g.send(lambda s, d, e: {"h": s["h"]}, src_feat={"h": g.node_feat["feature"]})
+    out = g.recv(lambda m: m.reduce_sum(m["h"]), msg).cpu().numpy()
+    want = O.recv(np.array(k["edges"]), k["num_nodes"], lambda m: m.reduce_sum(m["h"]),
+                  O.send(np.array(k["edges"]), lambda s, d, e: {"h": s["h"]}, src_feat={"h": x}))
+    assert (out == want).all()
+    out2 = g.send_recv(g.node_feat["feature"], "sum").cpu().numpy()
+    assert (out2 == want).all()
+
+
+# ---------------------------------------------------------------- random inputs vs oracle
+@pytest.mark.parametrize("D", [1, 3, 7, 16, 32, 100, 128, 200, 256, 512, 1433])
+def test_send_recv_sum_widths_bitexact(pgl, D):
+    n, e = 2000, 16000
+    edges = O.chung_lu_edges(n, e, exponent=0.3, seed=D)  # mild tail: no row above the hub threshold
+    rng = np.random.default_rng(D)
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    g = make_graph(pgl, edges, n)
+    assert g.adj_dst_index.max_degree <= 1024
+    out = g.send_recv(dev(x), "sum").cpu().numpy()
+    want = O.send_u_recv(x, edges[:, 0], edges[:, 1], "sum")
+    np.testing.assert_array_equal(out, want)  # same summation order => bit-exact
+
+
+@pytest.mark.parametrize("op_", ["sum", "mean", "max", "min"])
+@pytest.mark.parametrize("D", [8, 100, 128])
+def test_send_recv_ops_with_hubs(pgl, op_, D):
+    n, e = 20000, 400000
+    edges = O.chung_lu_edges(n, e, exponent=0.9, seed=11)  # heavy tail: hub rows exist
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    g = make_graph(pgl, edges, n)
+    assert g.adj_dst_index.max_degree > 4096
+    out = g.send_recv(dev(x), op_).cpu().numpy()
+    want = O.send_u_recv(x, edges[:, 0], edges[:, 1], op_)
+    if op_ in ("max", "min"):
+        np.testing.assert_array_equal(out, want)
+    else:
+        assert rel_err(out, want) <= RTOL
+        deg = O.adj_dst_index(edges, n)[0]
+        small = deg <= 1024
+        np.testing.assert_array_equal(out[small], want[small])  # non-hub rows stay bit-exact
+    # determinism: hub chunking is fixed
+    out2 = g.send_recv(dev(x), op_).cpu().numpy()
+    np.testing.assert_array_equal(out, out2)
+    # zero in-degree rows are exactly zero for every op
+    assert (out[O.adj_dst_index(edges, n)[0] == 0] == 0).all()
+
+
+def test_send_recv_empty_and_ragged(pgl):
+    g = make_graph(pgl, np.zeros((0, 2), np.int64), 6)
+    x = dev(np.ones((6, 12), np.float32))
+    for op_ in ("sum", "mean", "max", "min"):
+        assert (g.send_recv(x, op_).cpu().numpy() == 0).all()
+    g = make_graph(pgl, [(2, 2)] * 3000 + [(0, 5)], 6)  # one hub row, self loops, duplicates
+    xs = np.arange(6 * 4, dtype=np.float32).reshape(6, 4)
+    out = g.send_recv(dev(xs), "sum").cpu().numpy()
+    want = O.send_u_recv(xs, np.array([2] * 3000 + [0]), np.array([2] * 3000 + [5]), "sum")
+    assert rel_err(out, want) <= RTOL
+    out = g.send_recv(dev(xs), "mean").cpu().numpy()
+    np.testing.assert_allclose(out[2], xs[2], rtol=1e-6)
+
+
+def test_out_size(pgl):
+    n, e = 300, 2000
+    rng = np.random.default_rng(3)
+    edges = np.stack([rng.integers(0, n, e), rng.integers(0, 100, e)], 1)
+    x = rng.standard_normal((n, 24)).astype(np.float32)
+    g = make_graph(pgl, edges, n)
+    for osz in (100, 150, n, 400, 0, -1, None):
+        for op_ in ("sum", "mean"):
+            out = g.send_recv(dev(x), op_, out_size=osz).cpu().numpy()
+            want = O.send_u_recv(x, edges[:, 0], edges[:, 1], op_, out_size=osz)
+            assert out.shape == want.shape
+            np.testing.assert_array_equal(out, want)
+
+
+@pytest.mark.parametrize("mop", ["add", "sub", "mul", "div"])
+@pytest.mark.parametrize("rop", ["sum", "mean", "max", "min"])
+def test_send_ue_recv_random(pgl, mop, rop):
+    n, e, H, Dh = 500, 6000, 4, 8
+    edges = O.chung_lu_edges(n, e, exponent=0.5, seed=21)
+    rng = np.random.default_rng(22)
+    x = rng.standard_normal((n, H, Dh)).astype(np.float32)
+    g = make_graph(pgl, edges, n)
+    for yshape in ((e, H, 1), (e, H, Dh), (e, 1, 1), (e,)):
+        if len(yshape) == 1:
+            xx = x.reshape(n, H * Dh)
+        else:
+            xx = x
+        y = (rng.random(yshape).astype(np.float32) + 0.5)
+        out = g.send_ue_recv(dev(xx), dev(y), mop, rop).cpu().numpy()
+        want = O.send_ue_recv(xx, y, edges[:, 0], edges[:, 1], mop, rop)
+        assert out.shape == want.shape
+        assert rel_err(out, want) <= RTOL, (mop, rop, yshape)
+
+
+def test_send_uv_random(pgl):
+    n, e = 400, 5000
+    edges = O.chung_lu_edges(n, e, seed=31)
+    rng = np.random.default_rng(32)
+    g = make_graph(pgl, edges, n)
+    for shape in ((n, 8), (n, 5), (n, 4, 16), (n,)):
+        x = rng.standard_normal(shape).astype(np.float32)
+        y = rng.standard_normal(shape).astype(np.float32) + 3.0
+        for mop in ("add", "sub", "mul", "div"):
+            out = g.send_uv(dev(x), dev(y), mop).cpu().numpy()
+            want = O.send_uv(x, y, edges[:, 0], edges[:, 1], mop)
+            assert out.shape == want.shape
+            np.testing.assert_array_equal(out, want)
+
+
+def test_segment_ops_random(pgl):
+    rng = np.random.default_rng(41)
+    e, d = 30000, 48
+    ids = np.sort(rng.integers(0, 900, e)).astype(np.int64)
+    ids[ids > 450] += 7  # gaps: absent ids give zero rows
+    data = rng.standard_normal((e, d)).astype(np.float32)
+    for op_ in ("sum", "mean", "max", "min"):
+        out = pgl.math.segment_pool(dev(data), dev(ids), op_).cpu().numpy()
+        want = O.segment_pool(data, ids, op_)
+        assert out.shape == want.shape
+        np.testing.assert_array_equal(out, want)
+    out = pgl.math.segment_softmax(dev(data), dev(ids)).cpu().numpy()
+    assert rel_err(out, O.segment_softmax(data, ids)) <= RTOL
+    # 1-D data
+    v = rng.standard_normal(e).astype(np.float32)
+    out = pgl.math.segment_softmax(dev(v), dev(ids)).cpu().numpy()
+    assert rel_err(out, O.segment_softmax(v, ids)) <= RTOL
+
+
+def test_recv_udf_reduce_variants(pgl):
+    n, e = 800, 9000
+    edges = O.chung_lu_edges(n, e, exponent=0.6, seed=51)
+    rng = np.random.default_rng(52)
+    x = rng.standard_normal((n, 20)).astype(np.float32)
+    ef = rng.standard_normal((e, 20)).astype(np.float32)
+    g = make_graph(pgl, edges, n)
+
+    def send_func(s, d, ed):
+        return {"h": s["h"] * ed["w"], "w": ed["w"]}
+
+    def o_send(s, d, ed):
+        return {"h": s["h"] * ed["w"], "w": ed["w"]}
+
+    msg = g.send(send_func, src_feat={"h": dev(x)}, edge_feat={"w": dev(ef)})
+    omsg = O.send(edges, o_send, src_feat={"h": x}, edge_feat={"w": ef})
+    for name in ("reduce_sum", "reduce_mean", "reduce_max", "reduce_min"):
+        for mode in ("dst", "src"):
+            out = g.recv(lambda m: getattr(m, name)(m["h"]), msg, recv_mode=mode).cpu().numpy()
+            want = O.recv(edges, n, lambda m: getattr(m, name)(m["h"]), omsg, recv_mode=mode)
+            np.testing.assert_array_equal(out, want)
+    # the docstring example of Message.edge_expand (reference message.py:141-153)
+    def recv_func(m):
+        value = m["h"]
+        mx = m.edge_expand(m.reduce_max(value))
+        return m.reduce_sum(value - mx)
+
+    out = g.recv(recv_func, msg).cpu().numpy()
+    want = O.recv(edges, n, recv_func, omsg)
+    assert rel_err(out, want) <= RTOL
+    out = g.recv(lambda m: m.reduce_sum(m.reduce_softmax(m["h"]) * m["w"]), msg).cpu().numpy()
+    want = O.recv(edges, n, lambda m: m.reduce_sum(m.reduce_softmax(m["h"]) * m["w"]), omsg)
+    assert rel_err(out, want) <= RTOL
+
+
+def test_edge_softmax_random_with_hubs(pgl):
+    import pgl_b200.nn.functional as F
+    n, e, H = 5000, 120000, 8
+    edges = O.chung_lu_edges(n, e, exponent=0.9, seed=61)
+    rng = np.random.default_rng(62)
+    g = make_graph(pgl, edges, n)
+    assert g.adj_dst_index.max_degree > 2048
+    for shape in ((e, H), (e,), (e, 3), (e, 40)):
+        lg = (rng.standard_normal(shape) * 3).astype(np.float32)
+        for by in ("dst", "src"):
+            out = F.edge_softmax(g, dev(lg), norm_by=by).cpu().numpy()
+            want = O.edge_softmax(edges, n, lg, by)
+            assert rel_err(out, want) <= RTOL, (shape, by)
+
+
+def test_degree_norm(pgl):
+    import pgl_b200.nn.functional as F
+    edges = O.chung_lu_edges(3000, 40000, seed=71)
+    g = make_graph(pgl, edges, 3000)
+    out = F.degree_norm(g).cpu().numpy()
+    want = O.degree_norm(O.adj_dst_index(edges, 3000)[0])
+    assert out.shape == want.shape == (3000, 1)
+    np.testing.assert_allclose(out, want, rtol=2e-7)
+    out = F.degree_norm(g, "outdegree").cpu().numpy()
+    np.testing.assert_allclose(out, O.degree_norm(O.adj_src_index(edges, 3000)[0]), rtol=2e-7)
+
+
+# ---------------------------------------------------------------- conv layers vs oracle
+def _w(rng, *shape):
+    return (rng.standard_normal(shape) * 0.3).astype(np.float32)
+
+
+def test_gcn_conv_forward(pgl):
+    n, e = 1500, 12000
+    edges = O.chung_lu_edges(n, e, seed=81)
+    rng = np.random.default_rng(82)
+    g = make_graph(pgl, edges, n)
+    for fin, fout in ((64, 16), (16, 64), (32, 32)):
+        x = rng.standard_normal((n, fin)).astype(np.float32)
+        w, b = _w(rng, fin, fout), _w(rng, fout)
+        for normed in (True, False):
+            conv = pgl.nn.GCNConv(fin, fout, activation="relu", norm=normed).cuda()
+            with torch.no_grad():
+                conv.linear.weight.copy_(dev(w))
+                conv.bias.copy_(dev(b))
+                out = conv(g, dev(x)).cpu().numpy()
+            want = O.gcn_conv(edges, n, x, w, b, activation="relu", norm=normed)
+            assert rel_err(out, want) <= RTOL, (fin, fout, normed)
+
+
+def test_graphsage_conv_forward(pgl):
+    n, e = 1200, 10000
+    edges = O.chung_lu_edges(n, e, seed=91)
+    rng = np.random.default_rng(92)
+    g = make_graph(pgl, edges, n)
+    x = rng.standard_normal((n, 100)).astype(np.float32)
+    for aggr in ("sum", "mean", "max", "min"):
+        conv = pgl.nn.GraphSageConv(100, 32, aggr_func=aggr).cuda()
+        ws, bs, wn, bn = _w(rng, 100, 32), _w(rng, 32), _w(rng, 100, 32), _w(rng, 32)
+        with torch.no_grad():
+            conv.self_linear.weight.copy_(dev(ws)); conv.self_linear.bias.copy_(dev(bs))
+            conv.neigh_linear.weight.copy_(dev(wn)); conv.neigh_linear.bias.copy_(dev(bn))
+            out = conv(g, dev(x), act="relu").cpu().numpy()
+        want = O.graphsage_conv(edges, x, x, ws, bs, wn, bn, aggr, act="relu")
+        assert rel_err(out, want) <= RTOL, aggr
+
+
+def test_gat_conv_forward(pgl):
+    n, e, H, Dh = 1000, 9000, 8, 16
+    edges = O.chung_lu_edges(n, e, seed=101)
+    rng = np.random.default_rng(102)
+    g = make_graph(pgl, edges, n)
+    x = rng.standard_normal((n, 64)).astype(np.float32)
+    w, b = _w(rng, 64, H * Dh), _w(rng, H * Dh)
+    wsrc, wdst = _w(rng, H, Dh), _w(rng, H, Dh)
+    for concat in (True, False):
+        conv = pgl.nn.GATConv(64, Dh, feat_drop=0, attn_drop=0, num_heads=H, concat=concat).cuda()
+        with torch.no_grad():
+            conv.linear.weight.copy_(dev(w)); conv.linear.bias.copy_(dev(b))
+            conv.weight_src.copy_(dev(wsrc)); conv.weight_dst.copy_(dev(wdst))
+            out = conv(g, dev(x)).cpu().numpy()
+        want = O.gat_conv(edges, n, x, w, b, wsrc, wdst, H, Dh, concat=concat)
+        assert out.shape == want.shape
+        assert rel_err(out, want) <= RTOL
+
+
+def test_backward_sum_mean_vs_torch_reference(pgl):
+    """Gradient of the fused aggregation against plain torch fp32 autograd (index_add)."""
+    n, e, d = 700, 8000, 24
+    edges = O.chung_lu_edges(n, e, exponent=0.9, seed=111)
+    g = make_graph(pgl, edges, n)
+    src, dst = dev(edges[:, 0]), dev(edges[:, 1])
+    for op_ in ("sum", "mean"):
+        x1 = torch.randn(n, d, device="cuda", requires_grad=True)
+        x2 = x1.detach().clone().requires_grad_(True)
+        go = torch.randn(n, d, device="cuda")
+        g.send_recv(x1, op_).backward(go)
+        ref = torch.zeros(n, d, device="cuda").index_add_(0, dst, x2[src])
+        if op_ == "mean":
+            cnt = torch.zeros(n, device="cuda").index_add_(0, dst, torch.ones(e, device="cuda"))
+            ref = ref / cnt.clamp(min=1).unsqueeze(1)
+        ref.backward(go)
+        assert rel_err(x1.grad.cpu().numpy(), x2.grad.cpu().numpy()) <= RTOL
+
+
+def test_cpu_tensor_rejected(pgl):
+    g = make_graph(pgl, [(0, 1), (1, 2)], 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        g.send_recv(torch.zeros(3, 4), "sum")
+
+
+def test_full_size_properties(pgl):
+    """Size-independent properties at a size the numpy oracle cannot finish quickly:
+    linearity, checksum (sum over rows == sum over messages), mean*deg == sum."""
+    n, e, d = 1_000_000, 10_000_000, 128
+    edges = O.chung_lu_edges(n, e, seed=121)
+    ed = dev(edges)
+    g = pgl.Graph(edges=ed, num_nodes=n)
+    x = torch.randn(n, d, device="cuda")
+    y = torch.randn(n, d, device="cuda")
+    a = g.send_recv(x, "sum")
+    b = g.send_recv(y, "sum")
+    c = g.send_recv(x + y, "sum")
+    assert rel_err((a + b).cpu().numpy(), c.cpu().numpy()) <= RTOL
+    outdeg = g.outdegree().to(torch.float64)
+    lhs = a.to(torch.float64).sum(0)
+    rhs = (x.to(torch.float64) * outdeg.unsqueeze(1)).sum(0)
+    assert rel_err(lhs.cpu().numpy(), rhs.cpu().numpy()) <= 1e-6
+    m = g.send_recv(x, "mean")
+    indeg = g.indegree().to(torch.float32).clamp(min=1).unsqueeze(1)
+    assert rel_err((m * indeg).cpu().numpy(), a.cpu().numpy()) <= RTOL
+    mx = g.send_recv(x, "max")
+    mn = g.send_recv(x, "min")
+    has = (g.indegree() > 0).unsqueeze(1)
+    assert bool(((mx >= m - 1e-4) | ~has).all()) and bool(((mn <= m + 1e-4) | ~has).all())
+    # C oracle on a 100k-row slice of the same problem: exact for non-hub rows
+    sub = 100_000
+    deg, sv, su, se, ip = O.adj_dst_index(edges, n)
+    rows = np.arange(sub)
+    xs = x.cpu().numpy()
+    want = np.zeros((sub, d), np.float32)
+    for r in rows[:2000]:
+        want[r] = xs[sv[ip[r]:ip[r + 1]]].sum(0, dtype=np.float64) if ip[r + 1] > ip[r] else 0
+    assert rel_err(a[:2000].cpu().numpy(), want[:2000]) <= RTOL
