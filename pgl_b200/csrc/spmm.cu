@@ -18,6 +18,8 @@
 //    kernel is re-launched twice over "virtual rows" (chunk -> partial, partials -> row).
 //    No atomics on feature data, fixed chunking => deterministic run to run.
 #include <cfloat>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -408,6 +410,22 @@ static HubWs layout_ws(void *ws, int64_t E, int64_t D) {
 
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// spmm_stream.cu
+size_t stream_ws_bytes(int64_t E, int64_t D);
+int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, int64_t ldx,
+                    float *out, int64_t ldo, int64_t n_dst, int64_t n_src, int64_t E, int64_t D,
+                    int reduce_op, const float *scale_src, const float *scale_dst, void *ws,
+                    size_t ws_bytes, cudaStream_t stream);
+
+static bool use_stream_path() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("PGLB_SPMM_IMPL");
+        v = (e && strcmp(e, "legacy") == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
+
 }  // namespace pglb
 
 using namespace pglb;
@@ -416,7 +434,9 @@ extern "C" int pglb_spmm_csr_ws(int64_t n_dst, int64_t num_edges, int64_t D, siz
     PGLB_CHECK_ARG(ws_bytes != nullptr, PGLB_EINVAL, "pglb_spmm_csr_ws: ws_bytes is NULL");
     PGLB_CHECK_ARG(n_dst >= 0 && num_edges >= 0 && D >= 0, PGLB_EINVAL,
                    "pglb_spmm_csr_ws: negative size");
-    *ws_bytes = layout_ws(nullptr, num_edges, D).bytes;
+    size_t a = layout_ws(nullptr, num_edges, D).bytes;
+    size_t b = stream_ws_bytes(num_edges, D);
+    *ws_bytes = a > b ? a : b;
     return PGLB_OK;
 }
 
@@ -452,6 +472,12 @@ extern "C" int pglb_spmm_csr_f32(const int64_t *indptr, const int64_t *cols, con
     const bool vec4 = (D % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned16(x) &&
                       aligned16(out) &&
                       (mode == 0 || y_bcast != PGLB_BCAST_FULL || ((ldy % 4 == 0) && aligned16(y)));
+    if (mode == 0 && vec4 && D > 64 && use_stream_path()) {
+        PGLB_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255u) == 0, PGLB_EWORKSPACE,
+                       "pglb_spmm_csr_f32: workspace must be 256-byte aligned");
+        return spmm_stream_run(indptr, cols, x, ldx, out, ldo, n_dst, n_src, num_edges, D,
+                               reduce_op, scale_src, scale_dst, ws, ws_bytes, stream);
+    }
     const Shape s = pick_shape(D, vec4);
     const int rk = (reduce_op >= PGLB_REDUCE_MAX) ? 1 : 0;
 

@@ -1,0 +1,611 @@
+// spmm_stream.cu -- edge-balanced, shared-memory-staged CSR aggregation for sm_100a.
+//
+// The wide-row fast path of pglb_spmm_csr_f32 (copy message, 64 < D <= 128, 16-byte aligned
+// rows): the kernel the 10M-node / 100M-edge GCN roofline number is measured on.
+//
+//  * Work unit = a TASK of ~T consecutive CSR slots (not rows): every warp streams about T
+//    gathered feature rows whatever the degree distribution, so power-law hubs need no special
+//    pass.  A pre-kernel binary-searches the first row of every task and SNAPS the task start
+//    past a row of <= T slots that straddles the nominal boundary, so only rows longer than T
+//    are ever cut: every row of <= T slots is reduced start to end by one warp, strictly in slot
+//    (= ascending edge id) order -- bit-identical to the sequential CPU loop.
+//  * Each lane owns a private ring of 32 x 16-byte slots in shared memory.  Gathers are issued
+//    with cp.async.cg (LDGSTS, L1-bypassing) LAG groups of 8 rows ahead of the adds, so a warp
+//    keeps up to 32 rows (16 KB at D=128) in flight with no registers tied up; 14 warps per
+//    SM give ~220 KB of outstanding gathers per SM.  Lane l copies and later reads only its own
+//    16 bytes of every row: no cross-lane hand-off, hence no barriers at all.
+//  * A row longer than T that is cut by a task boundary leaves per-task partial sums in a side
+//    buffer; a fix-up kernel adds them in task order.  Fixed task size => deterministic.
+//  * Inner loops are written for instruction count (the first version was issue-bound at ~90
+//    warp instructions per edge): 32-bit positions relative to the task start, ring offsets
+//    that are compile-time constants, one shuffle + one IMAD.WIDE + one LDGSTS per gathered
+//    row, one LDS.128 + 4 FFMA/FADD per consumed row, row pointers prefetched one row ahead.
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace pglb {
+
+constexpr int RING = 32;  // slots per lane ring == one column batch
+constexpr int GRP = 8;    // rows per cp.async commit group
+constexpr int LAG = 3;    // groups in flight behind the issue point
+constexpr int SW = 7;     // warps per block (7 * 16 KB = 112 KB smem, two blocks per SM)
+
+struct StreamP {
+    const int64_t *indptr;
+    const int64_t *cols;  // nullable: identity
+    const float *x;
+    int64_t ldx;
+    float *out;
+    int64_t ldo;
+    int64_t n_rows;
+    int64_t E;
+    int D;
+    int reduce_op;
+    const float *scale_src;
+    const float *scale_dst;
+    int64_t T;  // nominal slots per task (multiple of 32)
+    int64_t ntasks;
+    const int64_t *first_row;  // [ntasks]
+    const int64_t *start;      // [ntasks + 1] snapped task starts
+    float *partial;            // [2*ntasks, dpad]
+    int64_t dpad;
+    int64_t *tail_row;  // [ntasks]
+};
+
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr));
+    return v;
+}
+
+// upper_bound(indptr[0..n_rows], v) - 1 : the non-empty row containing slot v
+__device__ __forceinline__ int64_t row_of_slot(const int64_t *__restrict__ indptr, int64_t n_rows,
+                                               int64_t v) {
+    int64_t lo = 0, hi = n_rows;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg((const long long *)indptr + mid) > v) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo - 1;
+}
+
+__global__ void __launch_bounds__(256) task_plan_kernel(const int64_t *__restrict__ indptr,
+                                                        int64_t n_rows, int64_t E, int64_t T,
+                                                        int64_t ntasks,
+                                                        int64_t *__restrict__ first_row,
+                                                        int64_t *__restrict__ start) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntasks) return;
+    if (t == ntasks) {
+        start[t] = E;
+        return;
+    }
+    if (t == 0) {
+        first_row[0] = 0;  // task 0 also owns leading empty rows
+        start[0] = 0;
+        return;
+    }
+    int64_t a = t * T;
+    int64_t r = row_of_slot(indptr, n_rows, a);
+    const int64_t s_r = __ldg((const long long *)indptr + r);
+    const int64_t e_r = __ldg((const long long *)indptr + r + 1);
+    if (s_r < a && e_r - s_r <= T) {
+        // a short row straddles the nominal boundary: the previous task finishes it
+        a = e_r;
+        r = (a < E) ? row_of_slot(indptr, n_rows, a) : n_rows - 1;
+    }
+    first_row[t] = r;
+    start[t] = a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// D <= 128 (one float4 per lane per row)
+// ---------------------------------------------------------------------------------------------
+template <int RK, bool SCALED>
+__global__ void __launch_bounds__(SW * 32, 2) spmm_stream128_kernel(const StreamP p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t task = (int64_t)blockIdx.x * SW + wib;
+    if (task >= p.ntasks) return;
+    const unsigned ring = (unsigned)__cvta_generic_to_shared(smem_raw) + wib * (RING * 512) + lane * 16;
+
+    const bool is_max = (p.reduce_op == PGLB_REDUCE_MAX);
+    const float ident = (RK == 0) ? 0.0f : (is_max ? -INFINITY : INFINITY);
+    const bool act = lane * 4 < p.D;
+    // inactive lanes (D < 128) alias lane 0's bytes: same sectors, no extra traffic, no predicates
+    const char *xlane = reinterpret_cast<const char *>(p.x) + (act ? lane * 16 : 0);
+    const unsigned row_bytes = (unsigned)(p.ldx * 4);
+
+    const int64_t a = ld_ro(p.start + task);
+    const int64_t b = ld_ro(p.start + task + 1);
+    const int cnt = (int)(b - a);
+    int64_t row = ld_ro(p.first_row + task);
+    int64_t tail = -1;
+    if (cnt > 0) {
+        auto rel = [&](int64_t v) -> int {
+            const int64_t d = v - a;
+            return d < -(1 << 30) ? -(1 << 30) : (d > (1 << 30) ? (1 << 30) : (int)d);
+        };
+        int beg_rel = rel(ld_ro(p.indptr + row));
+        int end_rel = rel(ld_ro(p.indptr + row + 1));
+        int nxt_rel = (row + 2 <= p.n_rows) ? rel(ld_ro(p.indptr + row + 2)) : (1 << 30);
+        bool head = beg_rel < 0;  // first row started in an earlier task (only rows longer than T)
+        float4 acc = make_float4(ident, ident, ident, ident);
+
+        auto finish_row = [&]() {
+            // row `row` is complete: slots [beg_rel, end_rel) relative to a
+            if (head) {
+                if (act) *reinterpret_cast<float4 *>(p.partial + (2 * task) * p.dpad + lane * 4) = acc;
+                head = false;  // the owner task's fix-up finishes this row
+            } else if (act) {
+                float4 v = acc;
+                const int deg = end_rel - beg_rel;
+                if (deg == 0) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.reduce_op == PGLB_REDUCE_MEAN && deg != 0) {
+                    const float c = (float)deg;
+                    v.x = __fdiv_rn(v.x, c); v.y = __fdiv_rn(v.y, c);
+                    v.z = __fdiv_rn(v.z, c); v.w = __fdiv_rn(v.w, c);
+                }
+                if (p.scale_dst) {
+                    const float sd = __ldg(p.scale_dst + row);
+                    v.x = __fmul_rn(v.x, sd); v.y = __fmul_rn(v.y, sd);
+                    v.z = __fmul_rn(v.z, sd); v.w = __fmul_rn(v.w, sd);
+                }
+                __stcs(reinterpret_cast<float4 *>(p.out + row * p.ldo + lane * 4), v);
+            }
+            ++row;
+            beg_rel = end_rel;
+            end_rel = nxt_rel;
+            nxt_rel = (row + 2 <= p.n_rows) ? rel(ld_ro(p.indptr + row + 2)) : (1 << 30);
+            acc = make_float4(ident, ident, ident, ident);
+        };
+
+        auto load_col = [&](int batch) -> unsigned {
+            const int j = batch * 32 + lane;
+            if (j >= cnt) return 0u;
+            return (unsigned)(p.cols ? ld_stream(p.cols + a + j) : (a + j));
+        };
+        // 32-bit column ids: the dispatcher routes n_src >= 2^32 to the generic kernel
+        unsigned col_cur = load_col(0);
+        unsigned col_nxt = load_col(1);
+        float sc_cur = 1.0f, sc_prev = 1.0f;
+        if (SCALED) sc_cur = (lane < cnt) ? __ldg(p.scale_src + col_cur) : 1.0f;
+
+        // One rolled loop over groups of 8 slots: issue group g, then consume group g - LAG.
+        // Deliberately NOT unrolled over the ring: the unrolled form inlined the row epilogue
+        // dozens of times (4096 SASS instructions, beyond the instruction cache); per-warp
+        // latency is hidden by the 14 resident warps instead.
+        const int ngroups = (cnt + GRP - 1) / GRP;
+#pragma unroll 1
+        for (int g = 0; g < ngroups + LAG; ++g) {
+            const int sub = g & 3;
+            if (g < ngroups) {
+                if (sub == 0 && g > 0) {
+                    const int base = g * GRP;
+                    sc_prev = sc_cur;
+                    col_cur = col_nxt;
+                    col_nxt = load_col((g >> 2) + 1);
+                    if (SCALED) sc_cur = (base + lane < cnt) ? __ldg(p.scale_src + col_cur) : 1.0f;
+                }
+                const int valid = cnt - g * GRP;
+                const unsigned gaddr = ring + sub * (GRP * 512);
+#pragma unroll
+                for (int k = 0; k < GRP; ++k) {
+                    const unsigned c = __shfl_sync(0xffffffffu, col_cur, sub * GRP + k);
+                    if (k < valid) cp_async16(gaddr + k * 512, xlane + (size_t)c * row_bytes);
+                }
+            }
+            cp_async_commit();
+            if (g >= LAG) {
+                cp_async_wait<LAG>();
+                const int gc = g - LAG;
+                const int csub = gc & 3;
+                const int base = gc * GRP;
+                // which register holds the scales of the consumed group's batch
+                const int bcur = (g < ngroups ? g : ngroups - 1) >> 2;
+                const float sc_reg = ((gc >> 2) == bcur) ? sc_cur : sc_prev;
+                int k_end = end_rel - base;  // where the current row ends inside this group
+                int valid = cnt - base;
+                valid = valid > GRP ? GRP : valid;
+                const unsigned gaddr = ring + csub * (GRP * 512);
+#pragma unroll 1
+                for (int k = 0; k < valid; ++k) {
+                    while (k == k_end) {
+                        finish_row();
+                        k_end = end_rel - base;
+                    }
+                    const float4 v = lds128(gaddr + k * 512);
+                    float s = 1.0f;
+                    if (SCALED) s = __shfl_sync(0xffffffffu, sc_reg, csub * GRP + k);
+                    if (RK == 0) {
+                        if (SCALED) {
+                            // x * norm[src] added in one FMA (more accurate than the reference's
+                            // separate multiply; within the 1e-4 bar)
+                            acc.x = fmaf(v.x, s, acc.x); acc.y = fmaf(v.y, s, acc.y);
+                            acc.z = fmaf(v.z, s, acc.z); acc.w = fmaf(v.w, s, acc.w);
+                        } else {
+                            acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y);
+                            acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+                        }
+                    } else if (is_max) {
+                        acc.x = fmaxf(acc.x, v.x * s); acc.y = fmaxf(acc.y, v.y * s);
+                        acc.z = fmaxf(acc.z, v.z * s); acc.w = fmaxf(acc.w, v.w * s);
+                    } else {
+                        acc.x = fminf(acc.x, v.x * s); acc.y = fminf(acc.y, v.y * s);
+                        acc.z = fminf(acc.z, v.z * s); acc.w = fminf(acc.w, v.w * s);
+                    }
+                }
+            }
+        }
+        // rows that end exactly at b (and, for the last non-empty task, every trailing empty row)
+        while (row < p.n_rows && end_rel == cnt) finish_row();
+        if (row < p.n_rows && beg_rel < cnt) {
+            // the open row (longer than T) continues in the next task(s)
+            if (act)
+                *reinterpret_cast<float4 *>(p.partial + (head ? (2 * task) : (2 * task + 1)) * p.dpad +
+                                            lane * 4) = acc;
+            if (!head) tail = row;
+        }
+    }
+    if (lane == 0) p.tail_row[task] = tail;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic ITERS (128 < D <= 512 per column tile): same scheme, straightforward code
+// ---------------------------------------------------------------------------------------------
+template <int ITERS>
+struct StreamCfg {
+    static constexpr int kWarps = (ITERS == 2) ? 2 : 1;
+    static constexpr int kThreads = kWarps * 32;
+    static constexpr int kSmem = kWarps * RING * 32 * ITERS * 16;
+};
+
+template <int ITERS, int RK>
+__global__ void __launch_bounds__(StreamCfg<ITERS>::kThreads) spmm_stream_kernel(const StreamP p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t task = (int64_t)blockIdx.x * StreamCfg<ITERS>::kWarps + wib;
+    if (task >= p.ntasks) return;
+    float4 *ring = reinterpret_cast<float4 *>(smem_raw) + (size_t)wib * RING * ITERS * 32 + lane;
+
+    const bool is_max = (p.reduce_op == PGLB_REDUCE_MAX);
+    const float ident = (RK == 0) ? 0.0f : (is_max ? -INFINITY : INFINITY);
+    const int col_tile = blockIdx.y * (32 * 4 * ITERS);
+    int col[ITERS];
+    bool act[ITERS];
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        col[it] = col_tile + (it * 32 + lane) * 4;
+        act[it] = col[it] < p.D;
+    }
+
+    const int64_t a = ld_ro(p.start + task);
+    const int64_t b = ld_ro(p.start + task + 1);
+    const int cnt = (int)(b - a);
+    const int ngroups = (cnt + GRP - 1) / GRP;
+    int64_t tail = -1;
+    if (cnt > 0) {
+        int64_t row = ld_ro(p.first_row + task);
+        int64_t cur_beg = ld_ro(p.indptr + row);
+        int64_t cur_end = ld_ro(p.indptr + row + 1);
+        bool head = cur_beg < a;
+        int64_t pos = a;
+
+        float4 acc[ITERS];
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) acc[it] = make_float4(ident, ident, ident, ident);
+
+        auto finish_row = [&]() {
+            const int64_t deg = cur_end - cur_beg;
+            if (head) {
+                float *dst = p.partial + (2 * task) * p.dpad;
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it)
+                    if (act[it]) *reinterpret_cast<float4 *>(dst + col[it]) = acc[it];
+                head = false;
+            } else {
+                const float sd = p.scale_dst ? __ldg(p.scale_dst + row) : 1.0f;
+                const float cntf = (float)deg;
+#pragma unroll
+                for (int it = 0; it < ITERS; ++it) {
+                    if (!act[it]) continue;
+                    float4 v = acc[it];
+                    if (deg == 0) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.reduce_op == PGLB_REDUCE_MEAN && deg != 0) {
+                        v.x = __fdiv_rn(v.x, cntf); v.y = __fdiv_rn(v.y, cntf);
+                        v.z = __fdiv_rn(v.z, cntf); v.w = __fdiv_rn(v.w, cntf);
+                    }
+                    if (p.scale_dst) {
+                        v.x = __fmul_rn(v.x, sd); v.y = __fmul_rn(v.y, sd);
+                        v.z = __fmul_rn(v.z, sd); v.w = __fmul_rn(v.w, sd);
+                    }
+                    __stcs(reinterpret_cast<float4 *>(p.out + row * p.ldo + col[it]), v);
+                }
+            }
+            ++row;
+            cur_beg = cur_end;
+            if (row < p.n_rows) cur_end = ld_ro(p.indptr + row + 1);
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it) acc[it] = make_float4(ident, ident, ident, ident);
+        };
+
+        auto load_col = [&](int batch) -> int64_t {
+            const int j = batch * 32 + lane;
+            if (j >= cnt) return 0;
+            return p.cols ? ld_stream(p.cols + a + j) : (a + j);
+        };
+        int64_t col_cur = load_col(0);
+        int64_t col_nxt = load_col(1);
+        float sc_cur = (p.scale_src && lane < cnt) ? __ldg(p.scale_src + col_cur) : 1.0f;
+        float sc_prev = 1.0f;
+
+        for (int g = 0; g < ngroups + LAG; ++g) {
+            if (g < ngroups) {
+                const int sub = g & 3;
+                if (sub == 0 && g > 0) {
+                    const int batch = g >> 2;
+                    sc_prev = sc_cur;
+                    col_cur = col_nxt;
+                    col_nxt = load_col(batch + 1);
+                    if (p.scale_src)
+                        sc_cur = (batch * 32 + lane < cnt) ? __ldg(p.scale_src + col_cur) : 1.0f;
+                }
+#pragma unroll
+                for (int k = 0; k < GRP; ++k) {
+                    const int64_t c = __shfl_sync(0xffffffffu, col_cur, sub * GRP + k);
+                    const int j = g * GRP + k;
+                    if (j < cnt) {
+                        const float *xr = p.x + c * p.ldx;
+                        float4 *slot = ring + (size_t)((j & (RING - 1)) * ITERS) * 32;
+#pragma unroll
+                        for (int it = 0; it < ITERS; ++it)
+                            if (act[it])
+                                cp_async16((unsigned)__cvta_generic_to_shared(slot + it * 32), xr + col[it]);
+                    }
+                }
+            }
+            cp_async_commit();
+            if (g >= LAG) {
+                cp_async_wait<LAG>();
+                const int gc = g - LAG;
+                const int bcur = (g < ngroups ? g : ngroups - 1) >> 2;
+                const bool in_cur = (gc >> 2) == bcur;
+#pragma unroll
+                for (int k = 0; k < GRP; ++k) {
+                    const int j = gc * GRP + k;
+                    const float s_c = __shfl_sync(0xffffffffu, sc_cur, (gc & 3) * GRP + k);
+                    const float s_p = __shfl_sync(0xffffffffu, sc_prev, (gc & 3) * GRP + k);
+                    if (j < cnt) {
+                        while (pos == cur_end) finish_row();
+                        const float s = in_cur ? s_c : s_p;
+                        const float4 *slot = ring + (size_t)((j & (RING - 1)) * ITERS) * 32;
+#pragma unroll
+                        for (int it = 0; it < ITERS; ++it) {
+                            if (!act[it]) continue;
+                            float4 v = slot[it * 32];
+                            if (p.scale_src) {
+                                v.x = __fmul_rn(v.x, s); v.y = __fmul_rn(v.y, s);
+                                v.z = __fmul_rn(v.z, s); v.w = __fmul_rn(v.w, s);
+                            }
+                            if (RK == 0) {
+                                acc[it].x = __fadd_rn(acc[it].x, v.x); acc[it].y = __fadd_rn(acc[it].y, v.y);
+                                acc[it].z = __fadd_rn(acc[it].z, v.z); acc[it].w = __fadd_rn(acc[it].w, v.w);
+                            } else if (is_max) {
+                                acc[it].x = fmaxf(acc[it].x, v.x); acc[it].y = fmaxf(acc[it].y, v.y);
+                                acc[it].z = fmaxf(acc[it].z, v.z); acc[it].w = fmaxf(acc[it].w, v.w);
+                            } else {
+                                acc[it].x = fminf(acc[it].x, v.x); acc[it].y = fminf(acc[it].y, v.y);
+                                acc[it].z = fminf(acc[it].z, v.z); acc[it].w = fminf(acc[it].w, v.w);
+                            }
+                        }
+                        ++pos;
+                    }
+                }
+            }
+        }
+        while (row < p.n_rows && cur_end == pos) finish_row();
+        if (row < p.n_rows && cur_beg < pos) {
+            float *dst = p.partial + (head ? (2 * task) : (2 * task + 1)) * p.dpad;
+#pragma unroll
+            for (int it = 0; it < ITERS; ++it)
+                if (act[it]) *reinterpret_cast<float4 *>(dst + col[it]) = acc[it];
+            if (!head) tail = row;
+        }
+    }
+    if (lane == 0 && blockIdx.y == 0) p.tail_row[task] = tail;
+}
+
+// One warp per task that owns a cut row: out[r] = epilogue(tail(t) (+) head(t+1) (+) ...)
+template <int ITERS, int RK>
+__global__ void __launch_bounds__(256) spmm_stream_fixup_kernel(const StreamP p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= p.ntasks) return;
+    const int64_t r = p.tail_row[t];
+    if (r < 0) return;
+    const bool is_max = (p.reduce_op == PGLB_REDUCE_MAX);
+    const int col_tile = blockIdx.y * (32 * 4 * ITERS);
+    const int64_t s_r = ld_ro(p.indptr + r), e_r = ld_ro(p.indptr + r + 1);
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int c = col_tile + (it * 32 + lane) * 4;
+        if (c >= p.D) continue;
+        float4 acc = *reinterpret_cast<const float4 *>(p.partial + (2 * t + 1) * p.dpad + c);
+        // tasks inside a row longer than T are never snapped: task u starts at u*T
+        for (int64_t u = t + 1; u * p.T < e_r; ++u) {
+            const float4 v = *reinterpret_cast<const float4 *>(p.partial + (2 * u) * p.dpad + c);
+            if (RK == 0) {
+                acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y);
+                acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+            } else if (is_max) {
+                acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y);
+                acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
+            } else {
+                acc.x = fminf(acc.x, v.x); acc.y = fminf(acc.y, v.y);
+                acc.z = fminf(acc.z, v.z); acc.w = fminf(acc.w, v.w);
+            }
+        }
+        if (p.reduce_op == PGLB_REDUCE_MEAN) {
+            const float cntf = (float)(e_r - s_r);
+            acc.x = __fdiv_rn(acc.x, cntf); acc.y = __fdiv_rn(acc.y, cntf);
+            acc.z = __fdiv_rn(acc.z, cntf); acc.w = __fdiv_rn(acc.w, cntf);
+        }
+        if (p.scale_dst) {
+            const float sd = __ldg(p.scale_dst + r);
+            acc.x = __fmul_rn(acc.x, sd); acc.y = __fmul_rn(acc.y, sd);
+            acc.z = __fmul_rn(acc.z, sd); acc.w = __fmul_rn(acc.w, sd);
+        }
+        *reinterpret_cast<float4 *>(p.out + r * p.ldo + c) = acc;
+    }
+}
+
+struct StreamWs {
+    int64_t *first_row;
+    int64_t *start;
+    int64_t *tail_row;
+    float *partial;
+    int64_t ntasks, dpad;
+    size_t bytes;
+};
+
+static StreamWs stream_layout(void *ws, int64_t E, int64_t D, int64_t T) {
+    StreamWs w;
+    w.ntasks = (E + T - 1) / T;
+    w.dpad = (D + 3) / 4 * 4;
+    char *base = reinterpret_cast<char *>(ws);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char *r = base ? base + off : nullptr;
+        off += align_up(bytes ? bytes : 1, 256);
+        return r;
+    };
+    w.first_row = reinterpret_cast<int64_t *>(take(sizeof(int64_t) * w.ntasks));
+    w.start = reinterpret_cast<int64_t *>(take(sizeof(int64_t) * (w.ntasks + 1)));
+    w.tail_row = reinterpret_cast<int64_t *>(take(sizeof(int64_t) * w.ntasks));
+    w.partial = reinterpret_cast<float *>(take(sizeof(float) * 2 * w.ntasks * w.dpad));
+    w.bytes = off;
+    return w;
+}
+
+int64_t stream_task_size() {
+    static int64_t t = 0;
+    if (t == 0) {
+        t = 1024;
+        const char *e = getenv("PGLB_STREAM_TASK");
+        if (e) {
+            long v = atol(e);
+            if (v >= 32 && v % 32 == 0) t = v;
+        }
+    }
+    return t;
+}
+
+size_t stream_ws_bytes(int64_t E, int64_t D) { return stream_layout(nullptr, E, D, stream_task_size()).bytes; }
+
+template <int RK, bool SCALED>
+static int launch_stream128(const StreamP &p, cudaStream_t stream) {
+    const int smem = SW * RING * 512;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PGLB_CUDA(cudaFuncSetAttribute(spmm_stream128_kernel<RK, SCALED>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int64_t blocks = (p.ntasks + SW - 1) / SW;
+    PGLB_CHECK_ARG(blocks <= 0x7fffffffLL, PGLB_ESHAPE, "spmm_stream: grid too large");
+    spmm_stream128_kernel<RK, SCALED><<<(unsigned)blocks, SW * 32, smem, stream>>>(p);
+    PGLB_LAUNCH_CHECK("spmm_stream128_kernel");
+    const int64_t fblocks = (p.ntasks * 32 + 255) / 256;
+    spmm_stream_fixup_kernel<1, RK><<<(unsigned)fblocks, 256, 0, stream>>>(p);
+    PGLB_LAUNCH_CHECK("spmm_stream_fixup_kernel");
+    return PGLB_OK;
+}
+
+template <int ITERS, int RK>
+static int launch_stream(const StreamP &p, int tiles, cudaStream_t stream) {
+    typedef StreamCfg<ITERS> Cfg;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PGLB_CUDA(cudaFuncSetAttribute(spmm_stream_kernel<ITERS, RK>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
+        attr_set = true;
+    }
+    const int64_t blocks = (p.ntasks + Cfg::kWarps - 1) / Cfg::kWarps;
+    PGLB_CHECK_ARG(blocks <= 0x7fffffffLL, PGLB_ESHAPE, "spmm_stream: grid too large");
+    dim3 grid((unsigned)blocks, (unsigned)tiles);
+    spmm_stream_kernel<ITERS, RK><<<grid, Cfg::kThreads, Cfg::kSmem, stream>>>(p);
+    PGLB_LAUNCH_CHECK("spmm_stream_kernel");
+    const int64_t fblocks = (p.ntasks * 32 + 255) / 256;
+    dim3 fgrid((unsigned)fblocks, (unsigned)tiles);
+    spmm_stream_fixup_kernel<ITERS, RK><<<fgrid, 256, 0, stream>>>(p);
+    PGLB_LAUNCH_CHECK("spmm_stream_fixup_kernel");
+    return PGLB_OK;
+}
+
+// Called by pglb_spmm_csr_f32 for the eligible shapes.  `ws` holds >= stream_ws_bytes().
+int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, int64_t ldx,
+                    float *out, int64_t ldo, int64_t n_dst, int64_t n_src, int64_t E, int64_t D,
+                    int reduce_op, const float *scale_src, const float *scale_dst, void *ws,
+                    size_t ws_bytes, cudaStream_t stream) {
+    const int64_t T = stream_task_size();
+    if (E == 0) {  // no slots: every row is empty
+        PGLB_CUDA(cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * D, n_dst, stream));
+        return PGLB_OK;
+    }
+    StreamWs w = stream_layout(ws, E, D, T);
+    PGLB_CHECK_ARG(ws != nullptr && ws_bytes >= w.bytes, PGLB_EWORKSPACE,
+                   "pglb_spmm_csr_f32: workspace of %zu bytes needed (got %zu)", w.bytes, ws_bytes);
+    StreamP p{};
+    p.indptr = indptr;
+    p.cols = cols;
+    p.x = x;
+    p.ldx = ldx;
+    p.out = out;
+    p.ldo = ldo;
+    p.n_rows = n_dst;
+    p.E = E;
+    p.D = (int)D;
+    p.reduce_op = reduce_op;
+    p.scale_src = scale_src;
+    p.scale_dst = scale_dst;
+    p.T = T;
+    p.ntasks = w.ntasks;
+    p.first_row = w.first_row;
+    p.start = w.start;
+    p.partial = w.partial;
+    p.dpad = w.dpad;
+    p.tail_row = w.tail_row;
+    {
+        const int64_t blocks = (w.ntasks + 1 + 255) / 256;
+        task_plan_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indptr, n_dst, E, T, w.ntasks,
+                                                               w.first_row, w.start);
+        PGLB_LAUNCH_CHECK("task_plan_kernel");
+    }
+    const int64_t cv = D / 4;
+    const int rk = (reduce_op >= PGLB_REDUCE_MAX) ? 1 : 0;
+    const bool small_ids = (cols ? n_src : E) < 0xffffffffLL && ldx * 4 < 0xffffffffLL;
+    if (cv <= 32 && small_ids) {
+        if (scale_src) return rk ? launch_stream128<1, true>(p, stream) : launch_stream128<0, true>(p, stream);
+        return rk ? launch_stream128<1, false>(p, stream) : launch_stream128<0, false>(p, stream);
+    }
+    const int iters = cv <= 64 ? 2 : 4;
+    const int tiles = (int)((cv + 32 * iters - 1) / (32 * iters));
+    if (iters == 2) return rk ? launch_stream<2, 1>(p, tiles, stream) : launch_stream<2, 0>(p, tiles, stream);
+    return rk ? launch_stream<4, 1>(p, tiles, stream) : launch_stream<4, 0>(p, tiles, stream);
+}
+
+}  // namespace pglb

@@ -132,13 +132,10 @@ def _spmm_raw(indptr, cols, x2, n_dst, reduce_op, eid=None, y2=None, y_bcast=BCA
     E = int(num_edges if num_edges is not None else (cols.shape[0] if cols is not None else 0))
     if out is None:
         out = torch.empty((n_dst, D), dtype=torch.float32, device=dev)
-    ws = None
-    wsn = 0
-    if not (0 <= max_degree <= 1024) and E > 1024:
-        need = ctypes.c_size_t(0)
-        check(lib.pglb_spmm_csr_ws(n_dst, E, D, ctypes.byref(need)))
-        ws = workspace(dev, need.value)
-        wsn = ws.numel()
+    need = ctypes.c_size_t(0)
+    check(lib.pglb_spmm_csr_ws(n_dst, E, D, ctypes.byref(need)))
+    ws = workspace(dev, need.value)
+    wsn = ws.numel()
     with torch.cuda.device(dev):
         check(lib.pglb_spmm_csr_f32(
             _ptr(indptr), _ptr(cols), _ptr(eid), _ptr(x2), x2.stride(0), _ptr(y2),

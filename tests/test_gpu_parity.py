@@ -17,6 +17,17 @@ from oracle import oracle as O
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 RTOL = 1e-4
+# rows of <= TASK slots are reduced by one warp in slot order (bit-exact vs the sequential
+# oracle); longer rows may be cut into per-task partial sums (tolerance).  The env override is
+# the stress setting used to exercise the cut-row machinery on small graphs.
+TASK = int(os.environ.get("PGLB_STREAM_TASK", "1024"))
+
+
+def check(out, want, max_row):
+    if max_row <= TASK:
+        np.testing.assert_array_equal(out, want)
+    else:
+        assert rel_err(out, want) <= RTOL
 
 
 def rel_err(a, b):
@@ -228,7 +239,7 @@ def test_send_recv_sum_widths_bitexact(pgl, D):
     assert g.adj_dst_index.max_degree <= 1024
     out = g.send_recv(dev(x), "sum").cpu().numpy()
     want = O.send_u_recv(x, edges[:, 0], edges[:, 1], "sum")
-    np.testing.assert_array_equal(out, want)  # same summation order => bit-exact
+    check(out, want, g.adj_dst_index.max_degree)  # same summation order => bit-exact
 
 
 @pytest.mark.parametrize("op_", ["sum", "mean", "max", "min"])
@@ -247,8 +258,8 @@ def test_send_recv_ops_with_hubs(pgl, op_, D):
     else:
         assert rel_err(out, want) <= RTOL
         deg = O.adj_dst_index(edges, n)[0]
-        small = deg <= 1024
-        np.testing.assert_array_equal(out[small], want[small])  # non-hub rows stay bit-exact
+        small = deg <= min(TASK, 1024)
+        np.testing.assert_array_equal(out[small], want[small])  # uncut rows stay bit-exact
     # determinism: hub chunking is fixed
     out2 = g.send_recv(dev(x), op_).cpu().numpy()
     np.testing.assert_array_equal(out, out2)
@@ -281,7 +292,7 @@ def test_out_size(pgl):
             out = g.send_recv(dev(x), op_, out_size=osz).cpu().numpy()
             want = O.send_u_recv(x, edges[:, 0], edges[:, 1], op_, out_size=osz)
             assert out.shape == want.shape
-            np.testing.assert_array_equal(out, want)
+            check(out, want, g.adj_dst_index.max_degree)
 
 
 @pytest.mark.parametrize("mop", ["add", "sub", "mul", "div"])
@@ -329,7 +340,7 @@ def test_segment_ops_random(pgl):
         out = pgl.math.segment_pool(dev(data), dev(ids), op_).cpu().numpy()
         want = O.segment_pool(data, ids, op_)
         assert out.shape == want.shape
-        np.testing.assert_array_equal(out, want)
+        check(out, want, int(np.bincount(ids).max()))
     out = pgl.math.segment_softmax(dev(data), dev(ids)).cpu().numpy()
     assert rel_err(out, O.segment_softmax(data, ids)) <= RTOL
     # 1-D data
