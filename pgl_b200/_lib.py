@@ -46,7 +46,8 @@ _SIGS = {
     "pglb_segment_indptr": (c_int, [_p, _i64, _i64, _p, _p]),
     "pglb_spmm_csr_ws": (c_int, [_i64, _i64, _i64, POINTER(c_size_t)]),
     "pglb_spmm_csr_f32": (c_int, [_p, _p, _p, _p, _i64, _p, _i64, c_int, _p, _i64, _i64, _i64, _i64,
-                                  _i64, _i64, c_int, c_int, _p, _p, _i64, _p, c_size_t, _p]),
+                                  _i64, _i64, c_int, c_int, _p, _p, _p, _i64, _p, c_size_t, _p]),
+    "pglb_hot_sources": (c_int, [_p, _i64, _i64, _p, _i64, _p, _p]),
     "pglb_send_uv_f32": (c_int, [_p, _p, _p, _i64, _p, _i64, _i64, _i64, c_int, _p, _p]),
     "pglb_gather_rows_f32": (c_int, [_p, _i64, _p, _i64, _i64, _i64, _p, _i64, _p]),
     "pglb_scatter_rows_f32": (c_int, [_p, _i64, _p, _i64, _i64, _p, _i64, _p]),

@@ -414,8 +414,8 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 size_t stream_ws_bytes(int64_t E, int64_t D);
 int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, int64_t ldx,
                     float *out, int64_t ldo, int64_t n_dst, int64_t n_src, int64_t E, int64_t D,
-                    int reduce_op, const float *scale_src, const float *scale_dst, void *ws,
-                    size_t ws_bytes, cudaStream_t stream);
+                    int reduce_op, const float *scale_src, const float *scale_dst,
+                    const uint8_t *src_hot, void *ws, size_t ws_bytes, cudaStream_t stream);
 
 static bool use_stream_path() {
     static int v = -1;
@@ -445,8 +445,9 @@ extern "C" int pglb_spmm_csr_f32(const int64_t *indptr, const int64_t *cols, con
                                  int y_bcast, float *out, int64_t ldo, int64_t n_dst,
                                  int64_t n_src, int64_t num_edges, int64_t D, int64_t head_dim,
                                  int msg_op, int reduce_op, const float *scale_src,
-                                 const float *scale_dst, int64_t max_degree_hint, void *ws,
-                                 size_t ws_bytes, void *stream_) {
+                                 const float *scale_dst, const uint8_t *src_hot,
+                                 int64_t max_degree_hint, void *ws, size_t ws_bytes,
+                                 void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     PGLB_CHECK_ARG(n_dst >= 0 && n_src >= 0 && num_edges >= 0 && D >= 0, PGLB_EINVAL,
                    "pglb_spmm_csr_f32: negative size");
@@ -476,7 +477,7 @@ extern "C" int pglb_spmm_csr_f32(const int64_t *indptr, const int64_t *cols, con
         PGLB_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255u) == 0, PGLB_EWORKSPACE,
                        "pglb_spmm_csr_f32: workspace must be 256-byte aligned");
         return spmm_stream_run(indptr, cols, x, ldx, out, ldo, n_dst, n_src, num_edges, D,
-                               reduce_op, scale_src, scale_dst, ws, ws_bytes, stream);
+                               reduce_op, scale_src, scale_dst, src_hot, ws, ws_bytes, stream);
     }
     const Shape s = pick_shape(D, vec4);
     const int rk = (reduce_op >= PGLB_REDUCE_MAX) ? 1 : 0;

@@ -51,10 +51,26 @@ struct StreamP {
     float *partial;            // [2*ntasks, dpad]
     int64_t dpad;
     int64_t *tail_row;  // [ntasks]
+    const uint8_t *src_hot;  // nullable [n_src]: 1 = keep this source row in L2 (evict_last)
 };
 
 __device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16_hint(unsigned smem_dst, const void *gsrc, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(smem_dst),
+                 "l"(gsrc), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -113,8 +129,13 @@ __global__ void __launch_bounds__(256) task_plan_kernel(const int64_t *__restric
 // ---------------------------------------------------------------------------------------------
 // D <= 128 (one float4 per lane per row)
 // ---------------------------------------------------------------------------------------------
-template <int RK, bool SCALED>
+template <int RK, bool SCALED, bool HOT>
 __global__ void __launch_bounds__(SW * 32, 2) spmm_stream128_kernel(const StreamP p) {
+    // HOT: bit 31 of the staged column id carries the source's L2 policy (hub sources that are
+    // gathered again and again are kept with evict_last, the long tail streams with evict_first
+    // so that it cannot flush them).
+    const uint64_t pol_last = HOT ? policy_evict_last() : 0;
+    const uint64_t pol_first = HOT ? policy_evict_first() : 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -176,13 +197,15 @@ __global__ void __launch_bounds__(SW * 32, 2) spmm_stream128_kernel(const Stream
         auto load_col = [&](int batch) -> unsigned {
             const int j = batch * 32 + lane;
             if (j >= cnt) return 0u;
-            return (unsigned)(p.cols ? ld_stream(p.cols + a + j) : (a + j));
+            unsigned c = (unsigned)(p.cols ? ld_stream(p.cols + a + j) : (a + j));
+            if (HOT) c |= (unsigned)__ldg(p.src_hot + c) << 31;
+            return c;
         };
         // 32-bit column ids: the dispatcher routes n_src >= 2^32 to the generic kernel
         unsigned col_cur = load_col(0);
         unsigned col_nxt = load_col(1);
         float sc_cur = 1.0f, sc_prev = 1.0f;
-        if (SCALED) sc_cur = (lane < cnt) ? __ldg(p.scale_src + col_cur) : 1.0f;
+        if (SCALED) sc_cur = (lane < cnt) ? __ldg(p.scale_src + (col_cur & 0x7fffffffu)) : 1.0f;
 
         // One rolled loop over groups of 8 slots: issue group g, then consume group g - LAG.
         // Deliberately NOT unrolled over the ring: the unrolled form inlined the row epilogue
@@ -198,14 +221,22 @@ __global__ void __launch_bounds__(SW * 32, 2) spmm_stream128_kernel(const Stream
                     sc_prev = sc_cur;
                     col_cur = col_nxt;
                     col_nxt = load_col((g >> 2) + 1);
-                    if (SCALED) sc_cur = (base + lane < cnt) ? __ldg(p.scale_src + col_cur) : 1.0f;
+                    if (SCALED)
+                        sc_cur = (base + lane < cnt) ? __ldg(p.scale_src + (col_cur & 0x7fffffffu)) : 1.0f;
                 }
                 const int valid = cnt - g * GRP;
                 const unsigned gaddr = ring + sub * (GRP * 512);
 #pragma unroll
                 for (int k = 0; k < GRP; ++k) {
                     const unsigned c = __shfl_sync(0xffffffffu, col_cur, sub * GRP + k);
-                    if (k < valid) cp_async16(gaddr + k * 512, xlane + (size_t)c * row_bytes);
+                    if (k < valid) {
+                        if (HOT) {
+                            const uint64_t pol = (c >> 31) ? pol_last : pol_first;
+                            cp_async16_hint(gaddr + k * 512, xlane + (size_t)(c & 0x7fffffffu) * row_bytes, pol);
+                        } else {
+                            cp_async16(gaddr + k * 512, xlane + (size_t)c * row_bytes);
+                        }
+                    }
                 }
             }
             cp_async_commit();
@@ -445,9 +476,9 @@ __global__ void __launch_bounds__(256) spmm_stream_fixup_kernel(const StreamP p)
         const int c = col_tile + (it * 32 + lane) * 4;
         if (c >= p.D) continue;
         float4 acc = *reinterpret_cast<const float4 *>(p.partial + (2 * t + 1) * p.dpad + c);
-        // tasks inside a row longer than T are never snapped: task u starts at u*T
-        for (int64_t u = t + 1; u * p.T < e_r; ++u) {
-            const float4 v = *reinterpret_cast<const float4 *>(p.partial + (2 * u) * p.dpad + c);
+        // tasks inside a row longer than T are never snapped: task u starts at u*T.  Loads are
+        // issued 8 at a time (independent), the adds stay in task order.
+        auto comb = [&](const float4 v) {
             if (RK == 0) {
                 acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y);
                 acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
@@ -458,7 +489,19 @@ __global__ void __launch_bounds__(256) spmm_stream_fixup_kernel(const StreamP p)
                 acc.x = fminf(acc.x, v.x); acc.y = fminf(acc.y, v.y);
                 acc.z = fminf(acc.z, v.z); acc.w = fminf(acc.w, v.w);
             }
+        };
+        const int64_t u_end = (e_r + p.T - 1) / p.T;  // first task that starts at or after e_r
+        int64_t u = t + 1;
+        for (; u + 8 <= u_end; u += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                v[q] = *reinterpret_cast<const float4 *>(p.partial + (2 * (u + q)) * p.dpad + c);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) comb(v[q]);
         }
+        for (; u < u_end; ++u)
+            comb(*reinterpret_cast<const float4 *>(p.partial + (2 * u) * p.dpad + c));
         if (p.reduce_op == PGLB_REDUCE_MEAN) {
             const float cntf = (float)(e_r - s_r);
             acc.x = __fdiv_rn(acc.x, cntf); acc.y = __fdiv_rn(acc.y, cntf);
@@ -504,7 +547,7 @@ static StreamWs stream_layout(void *ws, int64_t E, int64_t D, int64_t T) {
 int64_t stream_task_size() {
     static int64_t t = 0;
     if (t == 0) {
-        t = 1024;
+        t = 2048;
         const char *e = getenv("PGLB_STREAM_TASK");
         if (e) {
             long v = atol(e);
@@ -516,18 +559,18 @@ int64_t stream_task_size() {
 
 size_t stream_ws_bytes(int64_t E, int64_t D) { return stream_layout(nullptr, E, D, stream_task_size()).bytes; }
 
-template <int RK, bool SCALED>
+template <int RK, bool SCALED, bool HOT>
 static int launch_stream128(const StreamP &p, cudaStream_t stream) {
     const int smem = SW * RING * 512;
     static bool attr_set = false;
     if (!attr_set) {
-        PGLB_CUDA(cudaFuncSetAttribute(spmm_stream128_kernel<RK, SCALED>,
+        PGLB_CUDA(cudaFuncSetAttribute(spmm_stream128_kernel<RK, SCALED, HOT>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     const int64_t blocks = (p.ntasks + SW - 1) / SW;
     PGLB_CHECK_ARG(blocks <= 0x7fffffffLL, PGLB_ESHAPE, "spmm_stream: grid too large");
-    spmm_stream128_kernel<RK, SCALED><<<(unsigned)blocks, SW * 32, smem, stream>>>(p);
+    spmm_stream128_kernel<RK, SCALED, HOT><<<(unsigned)blocks, SW * 32, smem, stream>>>(p);
     PGLB_LAUNCH_CHECK("spmm_stream128_kernel");
     const int64_t fblocks = (p.ntasks * 32 + 255) / 256;
     spmm_stream_fixup_kernel<1, RK><<<(unsigned)fblocks, 256, 0, stream>>>(p);
@@ -559,8 +602,8 @@ static int launch_stream(const StreamP &p, int tiles, cudaStream_t stream) {
 // Called by pglb_spmm_csr_f32 for the eligible shapes.  `ws` holds >= stream_ws_bytes().
 int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, int64_t ldx,
                     float *out, int64_t ldo, int64_t n_dst, int64_t n_src, int64_t E, int64_t D,
-                    int reduce_op, const float *scale_src, const float *scale_dst, void *ws,
-                    size_t ws_bytes, cudaStream_t stream) {
+                    int reduce_op, const float *scale_src, const float *scale_dst,
+                    const uint8_t *src_hot, void *ws, size_t ws_bytes, cudaStream_t stream) {
     const int64_t T = stream_task_size();
     if (E == 0) {  // no slots: every row is empty
         PGLB_CUDA(cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * D, n_dst, stream));
@@ -589,6 +632,7 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
     p.partial = w.partial;
     p.dpad = w.dpad;
     p.tail_row = w.tail_row;
+    p.src_hot = src_hot;
     {
         const int64_t blocks = (w.ntasks + 1 + 255) / 256;
         task_plan_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indptr, n_dst, E, T, w.ntasks,
@@ -597,10 +641,16 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
     }
     const int64_t cv = D / 4;
     const int rk = (reduce_op >= PGLB_REDUCE_MAX) ? 1 : 0;
-    const bool small_ids = (cols ? n_src : E) < 0xffffffffLL && ldx * 4 < 0xffffffffLL;
+    const bool small_ids = (cols ? n_src : E) < 0x7fffffffLL && ldx * 4 < 0xffffffffLL;
     if (cv <= 32 && small_ids) {
-        if (scale_src) return rk ? launch_stream128<1, true>(p, stream) : launch_stream128<0, true>(p, stream);
-        return rk ? launch_stream128<1, false>(p, stream) : launch_stream128<0, false>(p, stream);
+        if (src_hot && cols) {
+            if (scale_src)
+                return rk ? launch_stream128<1, true, true>(p, stream) : launch_stream128<0, true, true>(p, stream);
+            return rk ? launch_stream128<1, false, true>(p, stream) : launch_stream128<0, false, true>(p, stream);
+        }
+        if (scale_src)
+            return rk ? launch_stream128<1, true, false>(p, stream) : launch_stream128<0, true, false>(p, stream);
+        return rk ? launch_stream128<1, false, false>(p, stream) : launch_stream128<0, false, false>(p, stream);
     }
     const int iters = cv <= 64 ? 2 : 4;
     const int tiles = (int)((cv + 32 * iters - 1) / (32 * iters));

@@ -3,6 +3,7 @@ torch, passes raw device pointers + the current CUDA stream to libpglb.  CUDA te
 every function raises on CPU tensors; there is no eager / CPU fallback on this path.
 """
 import ctypes
+import os
 
 import torch
 
@@ -126,7 +127,7 @@ def segment_indptr(segment_ids, num_segments):
 
 def _spmm_raw(indptr, cols, x2, n_dst, reduce_op, eid=None, y2=None, y_bcast=BCAST_FULL,
               head_dim=1, msg_op="copy", scale_src=None, scale_dst=None, max_degree=-1,
-              num_edges=None, out=None):
+              num_edges=None, out=None, src_hot=None):
     dev = x2.device
     D = int(x2.shape[1])
     E = int(num_edges if num_edges is not None else (cols.shape[0] if cols is not None else 0))
@@ -141,8 +142,34 @@ def _spmm_raw(indptr, cols, x2, n_dst, reduce_op, eid=None, y2=None, y_bcast=BCA
             _ptr(indptr), _ptr(cols), _ptr(eid), _ptr(x2), x2.stride(0), _ptr(y2),
             (y2.stride(0) if y2 is not None else 0), y_bcast, _ptr(out), out.stride(0), n_dst,
             int(x2.shape[0]), E, D, head_dim, MSG[msg_op], REDUCE[reduce_op], _ptr(scale_src),
-            _ptr(scale_dst), int(max_degree), _ptr(ws), wsn, _stream()))
+            _ptr(scale_dst), _ptr(src_hot), int(max_degree), _ptr(ws), wsn, _stream()))
     return out
+
+
+HOT_L2_BYTES = int(float(os.environ.get("PGLB_HOT_MB", "48")) * (1 << 20))
+
+
+def hot_sources(cols, n_src, row_bytes, budget_bytes=None):
+    """uint8 mask of the sources worth pinning in L2 for an aggregation with `row_bytes` rows:
+    the most frequently gathered rows, as many as fit in `budget_bytes` (default PGLB_HOT_MB,
+    48 MB of the 126 MB L2).  None when the whole feature matrix fits the budget or the hint is
+    disabled (PGLB_HOT_MB=0).  One-off per graph; cached by EdgeIndex."""
+    budget = HOT_L2_BYTES if budget_bytes is None else int(budget_bytes)
+    n_src = int(n_src)
+    E = int(cols.shape[0])
+    k = budget // max(int(row_bytes), 1)
+    if budget <= 0 or k <= 0 or n_src <= k or n_src >= (1 << 31) or E == 0:
+        return None
+    dev = cols.device
+    count = torch.empty(n_src, dtype=torch.int32, device=dev)
+    hot = torch.empty(n_src, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.pglb_hot_sources(_ptr(cols), E, n_src, _ptr(count), 1 << 40, _ptr(hot), _stream()))
+    thr = int(torch.topk(count, k, sorted=True).values[-1].item())
+    thr = max(thr, 2)  # a row gathered once gains nothing from residency
+    with torch.cuda.device(dev):
+        check(lib.pglb_hot_sources(_ptr(cols), E, n_src, _ptr(count), thr, _ptr(hot), _stream()))
+    return hot
 
 
 class _CopyAgg(torch.autograd.Function):
@@ -157,7 +184,8 @@ class _CopyAgg(torch.autograd.Function):
         ctx.scales = (scale_src, scale_dst)
         ctx.fwd = fwd
         return _spmm_raw(fwd["indptr"], fwd["cols"], x2, n_dst, reduce_op, scale_src=scale_src,
-                         scale_dst=scale_dst, max_degree=fwd.get("max_degree", -1))
+                         scale_dst=scale_dst, max_degree=fwd.get("max_degree", -1),
+                         src_hot=_hot_of(fwd, x2))
 
     @staticmethod
     def backward(ctx, g):
@@ -171,8 +199,18 @@ class _CopyAgg(torch.autograd.Function):
             inv = 1.0 / torch.clamp(ctx.fwd["degree"].to(torch.float32), min=1.0)
             s_in = inv if s_in is None else s_in * inv
         gx = _spmm_raw(bwd["indptr"], bwd["cols"], g, ctx.n_src, "sum", scale_src=s_in,
-                       scale_dst=scale_src, max_degree=bwd.get("max_degree", -1))
+                       scale_dst=scale_src, max_degree=bwd.get("max_degree", -1),
+                       src_hot=_hot_of(bwd, g))
         return gx, None, None, None, None, None, None
+
+
+def _hot_of(csr, x2):
+    """L2 residency hint for this (graph, row width), from the EdgeIndex cache."""
+    fn = csr.get("hot")
+    D = int(x2.shape[1])
+    if fn is None or D <= 64 or D > 128:
+        return None
+    return fn(int(x2.shape[0]), D * 4)
 
 
 def aggregate_copy(x, fwd, n_dst, reduce_op="sum", bwd=None, scale_src=None, scale_dst=None):
@@ -183,9 +221,9 @@ def aggregate_copy(x, fwd, n_dst, reduce_op="sum", bwd=None, scale_src=None, sca
     if reduce_op in ("sum", "mean") and x2.requires_grad and torch.is_grad_enabled():
         out = _CopyAgg.apply(x2, fwd, bwd, n_dst, reduce_op, scale_src, scale_dst)
     else:
-        out = _spmm_raw(fwd["indptr"], fwd["cols"], x2.detach() if reduce_op in ("sum", "mean") else x2,
-                        n_dst, reduce_op, scale_src=scale_src, scale_dst=scale_dst,
-                        max_degree=fwd.get("max_degree", -1))
+        out = _spmm_raw(fwd["indptr"], fwd["cols"], x2, n_dst, reduce_op, scale_src=scale_src,
+                        scale_dst=scale_dst, max_degree=fwd.get("max_degree", -1),
+                        src_hot=_hot_of(fwd, x2))
     return out.reshape((n_dst,) + tuple(shape[1:]))
 
 
