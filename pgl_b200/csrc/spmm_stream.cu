@@ -52,6 +52,7 @@ struct StreamP {
     int64_t dpad;
     int64_t *tail_row;  // [ntasks]
     const uint8_t *src_hot;  // nullable [n_src]: 1 = keep this source row in L2 (evict_last)
+    int hot_mode;            // 1: hot=evict_last cold=evict_first, 2: hot=last cold=normal, 3: hot=normal cold=first
 };
 
 __device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc) {
@@ -70,6 +71,11 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;\n" : "=l"(p));
     return p;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
@@ -134,8 +140,8 @@ __global__ void __launch_bounds__(SW * 32, 2) spmm_stream128_kernel(const Stream
     // HOT: bit 31 of the staged column id carries the source's L2 policy (hub sources that are
     // gathered again and again are kept with evict_last, the long tail streams with evict_first
     // so that it cannot flush them).
-    const uint64_t pol_last = HOT ? policy_evict_last() : 0;
-    const uint64_t pol_first = HOT ? policy_evict_first() : 0;
+    const uint64_t pol_last = !HOT ? 0 : (p.hot_mode == 3 ? policy_evict_normal() : policy_evict_last());
+    const uint64_t pol_first = !HOT ? 0 : (p.hot_mode == 2 ? policy_evict_normal() : policy_evict_first());
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -633,6 +639,15 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
     p.dpad = w.dpad;
     p.tail_row = w.tail_row;
     p.src_hot = src_hot;
+    {
+        static int mode = 0;
+        if (mode == 0) {
+            const char *e = getenv("PGLB_HOT_MODE");
+            mode = e ? atoi(e) : 1;
+            if (mode < 1 || mode > 3) mode = 1;
+        }
+        p.hot_mode = mode;
+    }
     {
         const int64_t blocks = (w.ntasks + 1 + 255) / 256;
         task_plan_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indptr, n_dst, E, T, w.ntasks,

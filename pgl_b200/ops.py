@@ -146,7 +146,7 @@ def _spmm_raw(indptr, cols, x2, n_dst, reduce_op, eid=None, y2=None, y_bcast=BCA
     return out
 
 
-HOT_L2_BYTES = int(float(os.environ.get("PGLB_HOT_MB", "48")) * (1 << 20))
+HOT_L2_BYTES = int(float(os.environ.get("PGLB_HOT_MB", "0")) * (1 << 20))
 
 
 def hot_sources(cols, n_src, row_bytes, budget_bytes=None):
@@ -327,8 +327,9 @@ def send_uv(x, y, src, dst, message_op="add"):
     return out.reshape((E,) + of)
 
 
-def gather_rows(x, index):
-    """paddle.gather(x, index, axis=0)."""
+def gather_rows(x, index, out=None):
+    """paddle.gather(x, index, axis=0).  The kernel is launched on the device of ``index`` /
+    ``out``; ``x`` may live on a peer GPU mapped into this process (NVLink P2P pull)."""
     require_cuda(x, index)
     index = _i64(index)
     n = int(index.shape[0])
@@ -336,12 +337,18 @@ def gather_rows(x, index):
         return x.index_select(0, index.contiguous())  # integer gathers (degree subsets): torch device op
     x2 = _f32_2d(x)
     D = int(x2.shape[1])
-    out = torch.empty((n, D), dtype=torch.float32, device=x2.device)
-    with torch.cuda.device(x2.device):
+    dev = index.device
+    if out is None:
+        out2 = torch.empty((n, D), dtype=torch.float32, device=dev)
+    else:
+        out2 = out.reshape(n, D) if out.dim() != 2 else out
+    with torch.cuda.device(dev):
         check(lib.pglb_gather_rows_f32(_ptr(x2), x2.stride(0), _ptr(index),
-                                       max(index.stride(0), 1) if n else 1, n, D, _ptr(out),
-                                       out.stride(0), _stream()))
-    return out.reshape((n,) + tuple(x.shape[1:]))
+                                       max(index.stride(0), 1) if n else 1, n, D, _ptr(out2),
+                                       out2.stride(0), _stream()))
+    if out is not None:
+        return out
+    return out2.reshape((n,) + tuple(x.shape[1:]))
 
 
 def scatter_rows(init, index, updates):

@@ -1,0 +1,53 @@
+"""torchrun check of the partition + halo path against the oracle (N GPUs):
+    python -m torch.distributed.run --nproc-per-node 2 scripts/check_sharded.py [nccl|p2p]"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    mode = sys.argv[1] if len(sys.argv) > 1 else "nccl"
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from oracle import oracle as O
+    from pgl_b200.distributed import ShardedGraph
+    n, e, d = 50000, 600000, 128
+    edges = O.chung_lu_edges(n, e, exponent=0.8, seed=3)
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    deg = O.adj_dst_index(edges, n)[0]
+    nrm = O.degree_norm(deg)
+    want = O.send_u_recv(x * nrm, edges[:, 0], edges[:, 1], "sum") * nrm
+    for method in ("block", "metis"):
+        sg = ShardedGraph.from_global_edges(torch.from_numpy(edges).to(dev), n, world, rank,
+                                            method=method, mode=mode)
+        ids = np.arange(n) if sg.new_id is None else sg.new_id
+        x2 = np.empty_like(x); x2[ids] = x
+        w2 = np.empty_like(want); w2[ids] = want
+        lo, hi = sg.plan.lo, sg.plan.hi
+        x_ext, x_local = sg.features(d)
+        x_local.copy_(torch.from_numpy(x2[lo:hi]).to(dev))
+        out = sg.gcn_aggregate(x_local).cpu().numpy()
+        err = np.abs(out - w2[lo:hi]).max() / np.abs(w2).max()
+        out_s = sg.send_recv(x_local, "mean").cpu().numpy()
+        wm = O.send_u_recv(x, edges[:, 0], edges[:, 1], "mean"); wm2 = np.empty_like(wm); wm2[ids] = wm
+        err2 = np.abs(out_s - wm2[lo:hi]).max() / np.abs(wm2).max()
+        st = sg.stats()
+        print("rank %d %s/%s gcn_rel_err=%.2e mean_rel_err=%.2e %s" % (rank, method, mode, err, err2, st), flush=True)
+        assert err <= 1e-4 and err2 <= 1e-4
+        dist.barrier()
+    if rank == 0:
+        print("check_sharded OK", mode)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
