@@ -426,7 +426,7 @@ def main_ours(args):
                    "l2_hot_rows": int(hot.sum().item()) if hot is not None else 0},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
                      "frac": achieved / hbm_gbs, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes": b_alg, "kernel": "spmm_csr_kernel<4,32,1,0,0> (+ hub passes)",
+                     "algorithmic_bytes": b_alg, "kernel": "spmm_stream128_kernel<0,1> (+ task_plan + fix-up kernels)",
                      "kernel_ms_mean": kern_ms, "kernel_ms_p10": per[len(per) // 10],
                      "kernel_ms_p90": per[(len(per) * 9) // 10]},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
