@@ -45,7 +45,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--partition", default="block", choices=["block", "metis"])
-    ap.add_argument("--halo", default=os.environ.get("PGLB_HALO_MODE", "nccl"), choices=["nccl", "p2p"])
+    ap.add_argument("--halo", default=os.environ.get("PGLB_HALO_MODE", "p2p"), choices=["nccl", "p2p"])
+    ap.add_argument("--no-overlap", action="store_true")
     return ap.parse_args()
 
 
@@ -289,7 +290,7 @@ def main_ours(args):
     if world > 1:
         from pgl_b200.distributed import ShardedGraph
         sg = ShardedGraph.from_global_edges(edges, n, world, rank, method=args.partition,
-                                            mode=args.halo)
+                                            mode=args.halo, overlap=not args.no_overlap)
         del edges
         torch.cuda.empty_cache()
         result = bench_sharded(args, torch, dist, pgl, sg, dev, world, rank, hbm_gbs, peak_src)

@@ -128,8 +128,12 @@ int pglb_spmm_csr_f32(const int64_t *indptr, const int64_t *cols, const int64_t 
                       float *out, int64_t ldo, int64_t n_dst, int64_t n_src,
                       int64_t num_edges, int64_t D, int64_t head_dim, int msg_op,
                       int reduce_op, const float *scale_src, const float *scale_dst,
-                      const uint8_t *src_hot, int64_t max_degree_hint, void *ws, size_t ws_bytes,
-                      void *stream);
+                      const uint8_t *src_hot, int64_t max_degree_hint, int flags, void *ws,
+                      size_t ws_bytes, void *stream);
+/* flags of pglb_spmm_csr_f32 */
+#define PGLB_SPMM_ACCUMULATE 1 /* SUM only: out[d] = (out[d] + sum of messages) * scale_dst[d];
+                                  lets a caller aggregate one edge subset while the feature rows of
+                                  another subset (halo rows) are still in flight */
 
 /* L2 residency hint for pglb_spmm_csr_f32: counts how often every source occurs in cols[E]
  * (count[n_src], int32, zeroed by the call) and sets hot[i] = count[i] >= min_count. */
@@ -167,6 +171,18 @@ int pglb_edge_softmax_csr_f32(const int64_t *indptr, const int64_t *eid, const f
 
 /* norm[i] = clip(float(degree[i]), 1)^-0.5 ; GF.degree_norm (graph_op.py:46-55) */
 int pglb_degree_norm_f32(const int64_t *degree, int64_t n, float *norm, void *stream);
+
+/* ------------------------------------------------------------------------------------
+ * Peer-mappable device buffers for the multi-GPU halo pull (NVLink P2P, one process per GPU).
+ * The only place the library allocates: cudaMalloc'ed buffers whose CUDA IPC handle (64 bytes)
+ * other ranks open under THEIR device with pglb_ipc_open; kernels such as pglb_gather_rows_f32
+ * then read the owner's HBM directly.  No reference counterpart (the reference replicates all
+ * features on every GPU, pgl/graph.py:1410-1553).
+ * ---------------------------------------------------------------------------------- */
+int pglb_ipc_alloc(size_t bytes, void **dev_ptr, void *handle64);
+int pglb_ipc_free(void *dev_ptr);
+int pglb_ipc_open(const void *handle64, void **peer_ptr);
+int pglb_ipc_close(void *peer_ptr);
 
 /* ------------------------------------------------------------------------------------
  * Host: METIS K-way behind the same call shape as graph_kernel.metis_partition

@@ -24,7 +24,7 @@ class PglbError(RuntimeError):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            "pgl_b200: %s not found. Build it first with `python -m pgl_b200.build` "
+            "pgl_b200: %s not found. Build it first with `python pgl_b200/build.py` "
             "(or __graft_entry__.build()); there is no CPU / eager fallback." % LIB_PATH)
     return ctypes.CDLL(LIB_PATH)
 
@@ -46,7 +46,11 @@ _SIGS = {
     "pglb_segment_indptr": (c_int, [_p, _i64, _i64, _p, _p]),
     "pglb_spmm_csr_ws": (c_int, [_i64, _i64, _i64, POINTER(c_size_t)]),
     "pglb_spmm_csr_f32": (c_int, [_p, _p, _p, _p, _i64, _p, _i64, c_int, _p, _i64, _i64, _i64, _i64,
-                                  _i64, _i64, c_int, c_int, _p, _p, _p, _i64, _p, c_size_t, _p]),
+                                  _i64, _i64, c_int, c_int, _p, _p, _p, _i64, c_int, _p, c_size_t, _p]),
+    "pglb_ipc_alloc": (c_int, [c_size_t, POINTER(c_void_p), _p]),
+    "pglb_ipc_free": (c_int, [_p]),
+    "pglb_ipc_open": (c_int, [_p, POINTER(c_void_p)]),
+    "pglb_ipc_close": (c_int, [_p]),
     "pglb_hot_sources": (c_int, [_p, _i64, _i64, _p, _i64, _p, _p]),
     "pglb_send_uv_f32": (c_int, [_p, _p, _p, _i64, _p, _i64, _i64, _i64, c_int, _p, _p]),
     "pglb_gather_rows_f32": (c_int, [_p, _i64, _p, _i64, _i64, _i64, _p, _i64, _p]),

@@ -1,6 +1,6 @@
 """Build libpglb.so (the C-ABI shared library, include/pglb.h) in-tree with nvcc for sm_100a.
 
-    python -m pgl_b200.build [--force]
+    python pgl_b200/build.py [--force]      (run as a script: importing the package needs the library)
 
 Also builds, when /root/reference is present, a METIS shared library from the reference's
 vendored third-party METIS 5.1.0 sources where they lie (IDXTYPEWIDTH 64) into

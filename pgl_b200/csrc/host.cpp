@@ -67,6 +67,51 @@ extern "C" int pglb_build_index_host(const int64_t *u, int64_t us, const int64_t
     return PGLB_OK;
 }
 
+// ---- peer-mappable buffers (CUDA IPC) ---------------------------------------------------------
+extern "C" int pglb_ipc_alloc(size_t bytes, void **dev_ptr, void *handle64) {
+    if (!dev_ptr || !handle64 || bytes == 0) return fail(PGLB_EINVAL, "pglb_ipc_alloc: bad args");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return cuda_fail(e, "cudaIpcGetMemHandle");
+    }
+    memcpy(handle64, &h, 64);
+    *dev_ptr = p;
+    return PGLB_OK;
+}
+
+extern "C" int pglb_ipc_free(void *dev_ptr) {
+    if (!dev_ptr) return PGLB_OK;
+    cudaError_t e = cudaFree(dev_ptr);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFree");
+    return PGLB_OK;
+}
+
+extern "C" int pglb_ipc_open(const void *handle64, void **peer_ptr) {
+    if (!handle64 || !peer_ptr) return fail(PGLB_EINVAL, "pglb_ipc_open: bad args");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void *p = nullptr;
+    // opened under the CALLER's current device: the mapping (and lazily enabled peer access)
+    // belongs to the GPU whose kernels will read it
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle");
+    *peer_ptr = p;
+    return PGLB_OK;
+}
+
+extern "C" int pglb_ipc_close(void *peer_ptr) {
+    if (!peer_ptr) return PGLB_OK;
+    cudaError_t e = cudaIpcCloseMemHandle(peer_ptr);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaIpcCloseMemHandle");
+    return PGLB_OK;
+}
+
 // ---- METIS through dlopen ---------------------------------------------------------------
 typedef int (*metis_part_fn)(int64_t *nvtxs, int64_t *ncon, int64_t *xadj, int64_t *adjncy,
                              int64_t *vwgt, int64_t *vsize, int64_t *adjwgt, int64_t *nparts,

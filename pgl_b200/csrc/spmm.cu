@@ -56,6 +56,7 @@ struct SpmmP {
     int64_t hub_threshold;
     unsigned long long *hub_count;
     int64_t *hub_rows;
+    int accumulate;  // SUM only: add the previous contents of out before the row epilogue
 };
 
 template <int VEC>
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(kThreads) spmm_csr_kernel(const SpmmP p) {
                 for (int j = 0; j < VEC; ++j) {
                     float a = acc[it][j];
                     if (deg == 0) a = 0.0f;
+                    if (p.accumulate) a = __fadd_rn(p.out[orow * p.ldo + col[it] + j], a);
                     if (p.reduce_op == PGLB_REDUCE_MEAN && deg != 0) a = __fdiv_rn(a, inv_cnt);
                     if (p.scale_dst) a = __fmul_rn(a, sd);
                     v[j] = a;
@@ -415,7 +417,8 @@ size_t stream_ws_bytes(int64_t E, int64_t D);
 int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, int64_t ldx,
                     float *out, int64_t ldo, int64_t n_dst, int64_t n_src, int64_t E, int64_t D,
                     int reduce_op, const float *scale_src, const float *scale_dst,
-                    const uint8_t *src_hot, void *ws, size_t ws_bytes, cudaStream_t stream);
+                    const uint8_t *src_hot, int accumulate, void *ws, size_t ws_bytes,
+                    cudaStream_t stream);
 
 static bool use_stream_path() {
     static int v = -1;
@@ -446,7 +449,7 @@ extern "C" int pglb_spmm_csr_f32(const int64_t *indptr, const int64_t *cols, con
                                  int64_t n_src, int64_t num_edges, int64_t D, int64_t head_dim,
                                  int msg_op, int reduce_op, const float *scale_src,
                                  const float *scale_dst, const uint8_t *src_hot,
-                                 int64_t max_degree_hint, void *ws, size_t ws_bytes,
+                                 int64_t max_degree_hint, int flags, void *ws, size_t ws_bytes,
                                  void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     PGLB_CHECK_ARG(n_dst >= 0 && n_src >= 0 && num_edges >= 0 && D >= 0, PGLB_EINVAL,
@@ -461,6 +464,9 @@ extern "C" int pglb_spmm_csr_f32(const int64_t *indptr, const int64_t *cols, con
     PGLB_CHECK_ARG(ldx >= D && ldo >= D, PGLB_ESHAPE,
                    "pglb_spmm_csr_f32: leading dimension smaller than D");
     PGLB_CHECK_ARG(D <= INT32_MAX, PGLB_ESHAPE, "pglb_spmm_csr_f32: D too large");
+    const int accumulate = (flags & PGLB_SPMM_ACCUMULATE) ? 1 : 0;
+    PGLB_CHECK_ARG(!accumulate || reduce_op == PGLB_REDUCE_SUM, PGLB_EUNSUPPORTED,
+                   "pglb_spmm_csr_f32: PGLB_SPMM_ACCUMULATE needs reduce_op SUM");
     const int mode = (msg_op == PGLB_MSG_COPY) ? 0 : 1;
     if (mode == 1) {
         PGLB_CHECK_ARG(y != nullptr, PGLB_EINVAL, "pglb_spmm_csr_f32: msg_op needs y");
@@ -473,11 +479,12 @@ extern "C" int pglb_spmm_csr_f32(const int64_t *indptr, const int64_t *cols, con
     const bool vec4 = (D % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned16(x) &&
                       aligned16(out) &&
                       (mode == 0 || y_bcast != PGLB_BCAST_FULL || ((ldy % 4 == 0) && aligned16(y)));
-    if (mode == 0 && vec4 && D > 64 && use_stream_path()) {
+    if (mode == 0 && vec4 && D > 64 && num_edges > 0 && use_stream_path()) {
         PGLB_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255u) == 0, PGLB_EWORKSPACE,
                        "pglb_spmm_csr_f32: workspace must be 256-byte aligned");
         return spmm_stream_run(indptr, cols, x, ldx, out, ldo, n_dst, n_src, num_edges, D,
-                               reduce_op, scale_src, scale_dst, src_hot, ws, ws_bytes, stream);
+                               reduce_op, scale_src, scale_dst, src_hot, accumulate, ws, ws_bytes,
+                               stream);
     }
     const Shape s = pick_shape(D, vec4);
     const int rk = (reduce_op >= PGLB_REDUCE_MAX) ? 1 : 0;
@@ -521,6 +528,7 @@ extern "C" int pglb_spmm_csr_f32(const int64_t *indptr, const int64_t *cols, con
     p.hub_threshold = need_hub ? HUB_T : INT64_MAX;
     p.hub_count = h.hub_count;
     p.hub_rows = h.hub_rows;
+    p.accumulate = accumulate;
 
     const int64_t gpb = kThreads / s.g;
     {
@@ -548,6 +556,7 @@ extern "C" int pglb_spmm_csr_f32(const int64_t *indptr, const int64_t *cols, con
         p1.scale_dst = nullptr;
         p1.rpg = 1;
         p1.contig = 0;
+        p1.accumulate = 0;
         p1.hub_threshold = INT64_MAX;
         {
             int64_t blocks = (h.chunk_cap + gpb - 1) / gpb;

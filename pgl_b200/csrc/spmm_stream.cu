@@ -52,6 +52,7 @@ struct StreamP {
     int64_t dpad;
     int64_t *tail_row;  // [ntasks]
     const uint8_t *src_hot;  // nullable [n_src]: 1 = keep this source row in L2 (evict_last)
+    int accumulate;          // SUM only: out = (out_prev + sum) * scale_dst
     int hot_mode;            // 1: hot=evict_last cold=evict_first, 2: hot=last cold=normal, 3: hot=normal cold=first
 };
 
@@ -181,6 +182,11 @@ __global__ void __launch_bounds__(SW * 32, 2) spmm_stream128_kernel(const Stream
                 float4 v = acc;
                 const int deg = end_rel - beg_rel;
                 if (deg == 0) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.accumulate) {
+                    const float4 o = *reinterpret_cast<const float4 *>(p.out + row * p.ldo + lane * 4);
+                    v.x = __fadd_rn(o.x, v.x); v.y = __fadd_rn(o.y, v.y);
+                    v.z = __fadd_rn(o.z, v.z); v.w = __fadd_rn(o.w, v.w);
+                }
                 if (p.reduce_op == PGLB_REDUCE_MEAN && deg != 0) {
                     const float c = (float)deg;
                     v.x = __fdiv_rn(v.x, c); v.y = __fdiv_rn(v.y, c);
@@ -362,6 +368,11 @@ __global__ void __launch_bounds__(StreamCfg<ITERS>::kThreads) spmm_stream_kernel
                     if (!act[it]) continue;
                     float4 v = acc[it];
                     if (deg == 0) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (p.accumulate) {
+                        const float4 o = *reinterpret_cast<const float4 *>(p.out + row * p.ldo + col[it]);
+                        v.x = __fadd_rn(o.x, v.x); v.y = __fadd_rn(o.y, v.y);
+                        v.z = __fadd_rn(o.z, v.z); v.w = __fadd_rn(o.w, v.w);
+                    }
                     if (p.reduce_op == PGLB_REDUCE_MEAN && deg != 0) {
                         v.x = __fdiv_rn(v.x, cntf); v.y = __fdiv_rn(v.y, cntf);
                         v.z = __fdiv_rn(v.z, cntf); v.w = __fdiv_rn(v.w, cntf);
@@ -508,6 +519,11 @@ __global__ void __launch_bounds__(256) spmm_stream_fixup_kernel(const StreamP p)
         }
         for (; u < u_end; ++u)
             comb(*reinterpret_cast<const float4 *>(p.partial + (2 * u) * p.dpad + c));
+        if (p.accumulate) {
+            const float4 o = *reinterpret_cast<const float4 *>(p.out + r * p.ldo + c);
+            acc.x = __fadd_rn(o.x, acc.x); acc.y = __fadd_rn(o.y, acc.y);
+            acc.z = __fadd_rn(o.z, acc.z); acc.w = __fadd_rn(o.w, acc.w);
+        }
         if (p.reduce_op == PGLB_REDUCE_MEAN) {
             const float cntf = (float)(e_r - s_r);
             acc.x = __fdiv_rn(acc.x, cntf); acc.y = __fdiv_rn(acc.y, cntf);
@@ -609,12 +625,10 @@ static int launch_stream(const StreamP &p, int tiles, cudaStream_t stream) {
 int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, int64_t ldx,
                     float *out, int64_t ldo, int64_t n_dst, int64_t n_src, int64_t E, int64_t D,
                     int reduce_op, const float *scale_src, const float *scale_dst,
-                    const uint8_t *src_hot, void *ws, size_t ws_bytes, cudaStream_t stream) {
+                    const uint8_t *src_hot, int accumulate, void *ws, size_t ws_bytes,
+                    cudaStream_t stream) {
     const int64_t T = stream_task_size();
-    if (E == 0) {  // no slots: every row is empty
-        PGLB_CUDA(cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * D, n_dst, stream));
-        return PGLB_OK;
-    }
+    PGLB_CHECK_ARG(E > 0, PGLB_EINVAL, "spmm_stream_run: needs at least one slot");
     StreamWs w = stream_layout(ws, E, D, T);
     PGLB_CHECK_ARG(ws != nullptr && ws_bytes >= w.bytes, PGLB_EWORKSPACE,
                    "pglb_spmm_csr_f32: workspace of %zu bytes needed (got %zu)", w.bytes, ws_bytes);
@@ -639,6 +653,7 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
     p.dpad = w.dpad;
     p.tail_row = w.tail_row;
     p.src_hot = src_hot;
+    p.accumulate = accumulate;
     {
         static int mode = 0;
         if (mode == 0) {

@@ -12,14 +12,19 @@ class ShardedGraph(object):
     """Rank-local dst rows + all their in-edges; source features = [own rows | halo rows].
 
     ``mode="nccl"``: halo rows are packed by a gather kernel and moved with one NCCL
-    all-to-all.  ``mode="p2p"``: every rank maps its peers' feature buffers (CUDA IPC) and a
-    gather kernel pulls the halo rows straight out of the owners' HBM over NVLink -- no pack
-    pass, no staging buffer, one launch per peer, overlappable with the interior aggregation.
+    all-to-all.  ``mode="p2p"``: every rank maps its peers' feature buffers (CUDA IPC, opened
+    under its own device) and a gather kernel pulls the halo rows straight out of the owners'
+    HBM over NVLink -- no pack pass, no staging buffer, one launch per peer.
+
+    ``overlap=True`` splits the local CSR by source: edges whose source is owned locally are
+    aggregated on the compute stream WHILE the halo rows are in flight on a second stream; the
+    halo-source edges are then added on top (PGLB_SPMM_ACCUMULATE) with the row epilogue.
     """
 
-    def __init__(self, plan, mode="nccl"):
+    def __init__(self, plan, mode="nccl", overlap=True):
         self.plan = plan
         self.mode = mode
+        self.overlap = bool(overlap) and plan.world > 1
         self.rank, self.world = plan.rank, plan.world
         self.n_local, self.n_halo = plan.n_local, plan.n_halo
         self.device = plan.dst_local.device
@@ -28,16 +33,28 @@ class ShardedGraph(object):
         self.index = EdgeIndex.from_index(sorted_v=sv, sorted_u=su, sorted_eid=se, degree=deg,
                                           indptr=ip)
         self._csr = self.index.csr()
+        self._csr_loc = self._csr_halo = None
+        if self.overlap:
+            is_loc = plan.col_local < self.n_local
+            for name, m in (("_csr_loc", is_loc), ("_csr_halo", ~is_loc)):
+                d2, v2, u2, e2, p2 = ops.csr_build(plan.dst_local[m], plan.col_local[m], self.n_local)
+                ix = EdgeIndex.from_index(sorted_v=v2, sorted_u=u2, sorted_eid=e2, degree=d2, indptr=p2)
+                setattr(self, name, ix.csr())
         self._buffers = {}
+        self._ipc = {}
         self._peers = {}
         self._norm = None
         self._norm_ext = None
         self._halo_off = np.concatenate([[0], np.cumsum(plan.recv_counts)]).astype(np.int64)
+        self._pull_idx = [plan.halo_ids[int(self._halo_off[p]):int(self._halo_off[p + 1])] - plan.offsets[p]
+                          for p in range(self.world)]
+        self._comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
 
     # ------------------------------------------------------------------ construction
     @classmethod
     def from_global_edges(cls, edges, num_nodes, world, rank, method="block", part=None,
-                          mode="nccl", group=None):
+                          mode="nccl", overlap=True, group=None):
         """edges: [E, 2] int64 CUDA tensor with GLOBAL ids, identical on every rank.
         method "block": contiguous id blocks; "metis": pgl.partition.metis_partition of the
         symmetrised graph on rank 0 (host), broadcast, nodes relabelled so parts are
@@ -63,7 +80,7 @@ class ShardedGraph(object):
         else:
             offsets = block_offsets(n, world)
         plan = HaloPlan.build(edges, n, offsets, rank, world, group=group)
-        self = cls(plan, mode=mode)
+        self = cls(plan, mode=mode, overlap=overlap)
         self.new_id = new_id
         return self
 
@@ -72,50 +89,51 @@ class ShardedGraph(object):
         """(x_ext [n_local + n_halo, dim], x_local view of its first n_local rows).  Keep node
         features in x_local so that no copy is needed before an exchange."""
         if dim not in self._buffers:
-            x_ext = torch.empty((self.n_local + self.n_halo, dim), dtype=torch.float32,
-                                device=self.device)
-            self._buffers[dim] = x_ext
+            rows = self.n_local + self.n_halo
             if self.mode == "p2p" and self.world > 1:
-                self._map_peers(dim, x_ext)
+                buf = ops.IpcBuffer(max(rows, 1), dim, self.device)
+                self._ipc[dim] = buf
+                x_ext = buf.tensor[:rows]
+                handles = [None] * self.world
+                dist.all_gather_object(handles, buf.handle_bytes(), group=self.plan.group)
+                self._peers[dim] = [None if p == self.rank else ops.ipc_open(h, self.device)
+                                    for p, h in enumerate(handles)]
+                dist.barrier(group=self.plan.group)
+            else:
+                x_ext = torch.empty((rows, dim), dtype=torch.float32, device=self.device)
+            self._buffers[dim] = x_ext
         x_ext = self._buffers[dim]
         return x_ext, x_ext[: self.n_local]
 
-    def _map_peers(self, dim, x_ext):
-        from torch.multiprocessing.reductions import reduce_tensor
-        fn, args = reduce_tensor(x_ext)
-        gathered = [None] * self.world
-        dist.all_gather_object(gathered, (fn, args), group=self.plan.group)
-        peers = []
-        for p, (f, a) in enumerate(gathered):
-            peers.append(None if p == self.rank else f(*a))
-        self._peers[dim] = peers
-        # lists of rows to pull from every peer, in that peer's local numbering
-        self._pull_idx = []
-        for p in range(self.world):
-            lo, hi = int(self._halo_off[p]), int(self._halo_off[p + 1])
-            self._pull_idx.append(self.plan.halo_ids[lo:hi] - self.plan.offsets[p])
-        dist.barrier(group=self.plan.group)
+    def _sync_peers(self):
+        # a 4-byte all-reduce: orders every rank's stream behind every other rank's prior work
+        dist.all_reduce(self._flag, group=self.plan.group)
 
-    def exchange(self, x_local):
-        """[x_local | halo rows] for the current feature width."""
-        dim = int(x_local.shape[1])
-        x_ext, view = self.features(dim)
-        if x_local.data_ptr() != view.data_ptr():
-            view.copy_(x_local)
-        if self.world == 1:
-            return x_ext
+    def _move_halo(self, x_ext, dim):
+        """Enqueue the halo transfer on the CURRENT stream."""
+        view = x_ext[: self.n_local]
         if self.mode == "p2p":
-            dist.barrier(group=self.plan.group)  # owners' rows are final (stream ordered)
+            self._sync_peers()  # owners' rows are final (stream ordered)
             peers = self._peers[dim]
             for k in range(1, self.world):
                 p = (self.rank + k) % self.world  # stagger the peers
                 lo, hi = int(self._halo_off[p]), int(self._halo_off[p + 1])
                 if hi > lo:
-                    ops.gather_rows(peers[p][: self.plan.offsets[p + 1] - self.plan.offsets[p]],
-                                    self._pull_idx[p], out=x_ext[self.n_local + lo: self.n_local + hi])
-            dist.barrier(group=self.plan.group)  # nobody overwrites rows that are still being read
-            return x_ext
-        return self.plan.exchange(view, x_ext=x_ext, pack=ops.gather_rows)
+                    ops.gather_rows_ptr(peers[p], dim, self._pull_idx[p],
+                                        x_ext[self.n_local + lo: self.n_local + hi])
+            self._sync_peers()  # nobody overwrites rows that are still being read
+        else:
+            self.plan.exchange(view, x_ext=x_ext, pack=ops.gather_rows)
+
+    def exchange(self, x_local):
+        """[x_local | halo rows] for the current feature width (blocking in stream order)."""
+        dim = int(x_local.shape[1])
+        x_ext, view = self.features(dim)
+        if x_local.data_ptr() != view.data_ptr():
+            view.copy_(x_local)
+        if self.world > 1:
+            self._move_halo(x_ext, dim)
+        return x_ext
 
     # ------------------------------------------------------------------ aggregation
     def local_norm(self):
@@ -134,12 +152,29 @@ class ShardedGraph(object):
                 self._norm_ext = ext.reshape(-1).contiguous()
         return self._norm_ext
 
+    def _agg(self, csr, x_ext, reduce_op, scale_src, scale_dst, out=None, accumulate=False):
+        return ops._spmm_raw(csr["indptr"], csr["cols"], x_ext, self.n_local, reduce_op,
+                             scale_src=scale_src, scale_dst=scale_dst,
+                             max_degree=csr["max_degree"], out=out, accumulate=accumulate)
+
     def send_recv(self, x_local, reduce_op="sum", scale_src=None, scale_dst=None):
         """Graph.send_recv on the shard: out rows = owned nodes."""
+        if self.overlap and reduce_op == "sum":
+            dim = int(x_local.shape[1])
+            x_ext, view = self.features(dim)
+            if x_local.data_ptr() != view.data_ptr():
+                view.copy_(x_local)
+            main = torch.cuda.current_stream(self.device)
+            self._comm_stream.wait_stream(main)
+            with torch.cuda.stream(self._comm_stream):
+                self._move_halo(x_ext, dim)
+            # local-source edges while the halo rows travel
+            out = self._agg(self._csr_loc, x_ext, "sum", scale_src, None)
+            main.wait_stream(self._comm_stream)
+            return self._agg(self._csr_halo, x_ext, "sum", scale_src, scale_dst, out=out,
+                             accumulate=True)
         x_ext = self.exchange(x_local)
-        return ops._spmm_raw(self._csr["indptr"], self._csr["cols"], x_ext, self.n_local, reduce_op,
-                             scale_src=scale_src, scale_dst=scale_dst,
-                             max_degree=self._csr["max_degree"])
+        return self._agg(self._csr, x_ext, reduce_op, scale_src, scale_dst)
 
     def gcn_aggregate(self, x_local, norm_local=None):
         """norm * (A (norm * x)) on the shard (the GCNConv aggregation)."""
@@ -149,11 +184,15 @@ class ShardedGraph(object):
     def stats(self):
         s = self.plan.stats()
         s["mode"] = self.mode
+        s["overlap"] = self.overlap
         s["max_in_degree"] = int(self._csr["max_degree"])
+        if self._csr_loc is not None:
+            s["e_local_src"] = int(self._csr_loc["cols"].shape[0])
+            s["e_halo_src"] = int(self._csr_halo["cols"].shape[0])
         return s
 
     def time_split(self, x_local, norm_local=None, iters=3):
-        """Device-timed exchange vs aggregation on this rank (ms)."""
+        """Device-timed exchange vs (non-overlapped) aggregation on this rank (ms)."""
         ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
         self.gcn_aggregate(x_local)
         torch.cuda.synchronize()
@@ -165,9 +204,7 @@ class ShardedGraph(object):
             a.record()
             x_ext = self.exchange(x_local)
             b.record()
-            ops._spmm_raw(self._csr["indptr"], self._csr["cols"], x_ext, self.n_local, "sum",
-                          scale_src=self.ext_norm(), scale_dst=self.local_norm(),
-                          max_degree=self._csr["max_degree"])
+            self._agg(self._csr, x_ext, "sum", self.ext_norm(), self.local_norm())
             c.record()
             torch.cuda.synchronize()
             te += a.elapsed_time(b)

@@ -127,7 +127,7 @@ def segment_indptr(segment_ids, num_segments):
 
 def _spmm_raw(indptr, cols, x2, n_dst, reduce_op, eid=None, y2=None, y_bcast=BCAST_FULL,
               head_dim=1, msg_op="copy", scale_src=None, scale_dst=None, max_degree=-1,
-              num_edges=None, out=None, src_hot=None):
+              num_edges=None, out=None, src_hot=None, accumulate=False):
     dev = x2.device
     D = int(x2.shape[1])
     E = int(num_edges if num_edges is not None else (cols.shape[0] if cols is not None else 0))
@@ -142,7 +142,58 @@ def _spmm_raw(indptr, cols, x2, n_dst, reduce_op, eid=None, y2=None, y_bcast=BCA
             _ptr(indptr), _ptr(cols), _ptr(eid), _ptr(x2), x2.stride(0), _ptr(y2),
             (y2.stride(0) if y2 is not None else 0), y_bcast, _ptr(out), out.stride(0), n_dst,
             int(x2.shape[0]), E, D, head_dim, MSG[msg_op], REDUCE[reduce_op], _ptr(scale_src),
-            _ptr(scale_dst), _ptr(src_hot), int(max_degree), _ptr(ws), wsn, _stream()))
+            _ptr(scale_dst), _ptr(src_hot), int(max_degree), 1 if accumulate else 0, _ptr(ws), wsn,
+            _stream()))
+    return out
+
+
+class IpcBuffer(object):
+    """A cudaMalloc'ed float32 [rows, cols] buffer with a CUDA IPC handle (pglb_ipc_alloc), exposed
+    to torch zero-copy through __cuda_array_interface__.  Used for the multi-GPU feature buffer
+    whose rows peers pull over NVLink."""
+
+    def __init__(self, rows, cols, device):
+        self.shape = (int(rows), int(cols))
+        self.device = device
+        nbytes = max(self.shape[0] * self.shape[1] * 4, 256)
+        ptr = ctypes.c_void_p()
+        self.handle = ctypes.create_string_buffer(64)
+        with torch.cuda.device(device):
+            check(lib.pglb_ipc_alloc(nbytes, ctypes.byref(ptr), self.handle))
+        self.ptr = int(ptr.value)
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": "<f4",
+                                         "data": (self.ptr, False), "version": 2, "strides": None}
+        self.tensor = torch.as_tensor(self, device=device)
+
+    def handle_bytes(self):
+        return bytes(self.handle.raw)
+
+    def close(self):
+        if self.ptr:
+            self.tensor = None
+            lib.pglb_ipc_free(ctypes.c_void_p(self.ptr))
+            self.ptr = 0
+
+
+def ipc_open(handle_bytes, device):
+    """Map a peer's IpcBuffer under `device`; returns the raw device pointer (int)."""
+    ptr = ctypes.c_void_p()
+    buf = ctypes.create_string_buffer(handle_bytes, 64)
+    with torch.cuda.device(device):
+        check(lib.pglb_ipc_open(buf, ctypes.byref(ptr)))
+    return int(ptr.value)
+
+
+def gather_rows_ptr(src_ptr, ld, index, out):
+    """out[i] = src[index[i]] where src is a raw (possibly peer-mapped) float32 pointer."""
+    n = int(index.shape[0])
+    if n == 0:
+        return out
+    D = int(out.shape[1])
+    with torch.cuda.device(out.device):
+        check(lib.pglb_gather_rows_f32(ctypes.c_void_p(src_ptr), int(ld), _ptr(index),
+                                       max(index.stride(0), 1), n, D, _ptr(out), out.stride(0),
+                                       _stream()))
     return out
 
 

@@ -28,7 +28,8 @@ def main():
     want = O.send_u_recv(x * nrm, edges[:, 0], edges[:, 1], "sum") * nrm
     for method in ("block", "metis"):
         sg = ShardedGraph.from_global_edges(torch.from_numpy(edges).to(dev), n, world, rank,
-                                            method=method, mode=mode)
+                                            method=method, mode=mode,
+                                            overlap=(os.environ.get("OVERLAP", "1") == "1"))
         ids = np.arange(n) if sg.new_id is None else sg.new_id
         x2 = np.empty_like(x); x2[ids] = x
         w2 = np.empty_like(want); w2[ids] = want

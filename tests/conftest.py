@@ -15,8 +15,8 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     # build the native pieces once (no-ops when up to date; nvcc cross-compiles without a GPU)
     if shutil.which("nvcc"):
-        from pgl_b200 import build as pbuild
-        pbuild.build_all()
+        import __graft_entry__
+        __graft_entry__.load_builder().build_all()
     from oracle import build as obuild
     obuild.build_oracle_c()
     if os.path.isdir("/root/reference"):

@@ -33,7 +33,7 @@ def test_error_convention():
     assert lib.pglb_spmm_csr_ws(10, 100, 16, None) == -1
     # invalid enums / shapes are rejected without touching the device
     rc = lib.pglb_spmm_csr_f32(None, None, None, None, 4, None, 0, 0, None, 4, 10, 10, 5, 4, 1,
-                               0, 9, None, None, None, -1, None, 0, None)
+                               0, 9, None, None, None, -1, 0, None, 0, None)
     assert rc == -1 and b"reduce_op" in lib.pglb_last_error()
     rc = lib.pglb_send_uv_f32(None, None, None, 1, None, 1, 5, 4, 0, None, None)
     assert rc == -1
@@ -41,7 +41,7 @@ def test_error_convention():
         _lib.check(rc)
     # zero-sized problems are OK no-ops
     assert lib.pglb_spmm_csr_f32(None, None, None, None, 4, None, 0, 0, None, 4, 0, 0, 0, 4, 1, 0,
-                                 0, None, None, None, -1, None, 0, None) == 0
+                                 0, None, None, None, -1, 0, None, 0, None) == 0
 
 
 def test_build_index_host_vs_reference_golden():
