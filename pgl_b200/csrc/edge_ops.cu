@@ -48,6 +48,12 @@ __global__ void __launch_bounds__(256) send_uv_kernel(const float *__restrict__ 
 }
 
 // ---- gather / scatter rows -------------------------------------------------------------
+// Small, fixed footprint (2 blocks of 256 threads per SM) with 8 independent 16-byte loads in
+// flight per thread: ~9.7 MB outstanding chip-wide, enough to saturate HBM or an NVLink peer
+// (2 us x 770 GB/s = 1.5 MB), while leaving most of every SM to a concurrently running
+// aggregation kernel (the multi-GPU halo pull overlaps with the local-source aggregation).
+constexpr int MV_UNROLL = 8;
+
 template <int VEC, bool SCATTER>
 __global__ void __launch_bounds__(256) move_rows_kernel(const float *__restrict__ x, int64_t ldx,
                                                         const int64_t *__restrict__ index,
@@ -55,18 +61,33 @@ __global__ void __launch_bounds__(256) move_rows_kernel(const float *__restrict_
                                                         float *__restrict__ out, int64_t ldo) {
     const int dv = D / VEC;
     const int64_t total = n * dv;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / dv;
-        const int c = (int)(i - r * dv) * VEC;
-        const int64_t k = __ldg((const long long *)index + r * istride);
-        const int64_t rs = SCATTER ? r : k;
-        const int64_t rd = SCATTER ? k : r;
-        if (VEC == 4) {
-            *reinterpret_cast<float4 *>(out + rd * ldo + c) =
-                __ldg(reinterpret_cast<const float4 *>(x + rs * ldx + c));
-        } else {
-            out[rd * ldo + c] = __ldg(x + rs * ldx + c);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total;
+         i0 += stride * MV_UNROLL) {
+        float4 v4[MV_UNROLL];
+        float v1[MV_UNROLL];
+        int64_t dsto[MV_UNROLL];
+#pragma unroll
+        for (int u = 0; u < MV_UNROLL; ++u) {
+            const int64_t i = i0 + u * stride;
+            dsto[u] = -1;
+            if (i < total) {
+                const int64_t r = i / dv;
+                const int c = (int)(i - r * dv) * VEC;
+                const int64_t k = __ldg((const long long *)index + r * istride);
+                const int64_t rs = SCATTER ? r : k;
+                const int64_t rd = SCATTER ? k : r;
+                dsto[u] = rd * ldo + c;
+                if (VEC == 4) v4[u] = __ldg(reinterpret_cast<const float4 *>(x + rs * ldx + c));
+                else v1[u] = __ldg(x + rs * ldx + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < MV_UNROLL; ++u) {
+            if (dsto[u] >= 0) {
+                if (VEC == 4) *reinterpret_cast<float4 *>(out + dsto[u]) = v4[u];
+                else out[dsto[u]] = v1[u];
+            }
         }
     }
 }
@@ -175,6 +196,13 @@ __global__ void __launch_bounds__(256) degree_norm_kernel(const int64_t *__restr
 }
 
 static inline bool a16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline int grid_move(int64_t total) {
+    int64_t b = (total + 256 * MV_UNROLL - 1) / (256 * MV_UNROLL);
+    const int64_t cap = (int64_t)sm_count() * 2;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
 static inline int grid_for(int64_t total) {
     int64_t b = (total + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 32;
@@ -218,10 +246,10 @@ extern "C" int pglb_gather_rows_f32(const float *x, int64_t ldx, const int64_t *
     PGLB_CHECK_ARG(ldx >= D && ldo >= D && index_stride >= 1, PGLB_ESHAPE,
                    "pglb_gather_rows_f32: bad leading dimension / stride");
     if (D % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && a16(x) && a16(out))
-        move_rows_kernel<4, false><<<grid_for(n * (D / 4)), 256, 0, stream>>>(
+        move_rows_kernel<4, false><<<grid_move(n * (D / 4)), 256, 0, stream>>>(
             x, ldx, index, index_stride, n, (int)D, out, ldo);
     else
-        move_rows_kernel<1, false><<<grid_for(n * D), 256, 0, stream>>>(x, ldx, index, index_stride,
+        move_rows_kernel<1, false><<<grid_move(n * D), 256, 0, stream>>>(x, ldx, index, index_stride,
                                                                         n, (int)D, out, ldo);
     PGLB_LAUNCH_CHECK("gather_rows_kernel");
     return PGLB_OK;
@@ -235,10 +263,10 @@ extern "C" int pglb_scatter_rows_f32(const float *x, int64_t ldx, const int64_t 
     PGLB_CHECK_ARG(x && index && out, PGLB_EINVAL, "pglb_scatter_rows_f32: NULL pointer");
     PGLB_CHECK_ARG(ldx >= D && ldo >= D, PGLB_ESHAPE, "pglb_scatter_rows_f32: bad leading dimension");
     if (D % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && a16(x) && a16(out))
-        move_rows_kernel<4, true><<<grid_for(n * (D / 4)), 256, 0, stream>>>(x, ldx, index, 1, n,
+        move_rows_kernel<4, true><<<grid_move(n * (D / 4)), 256, 0, stream>>>(x, ldx, index, 1, n,
                                                                              (int)D, out, ldo);
     else
-        move_rows_kernel<1, true><<<grid_for(n * D), 256, 0, stream>>>(x, ldx, index, 1, n, (int)D,
+        move_rows_kernel<1, true><<<grid_move(n * D), 256, 0, stream>>>(x, ldx, index, 1, n, (int)D,
                                                                        out, ldo);
     PGLB_LAUNCH_CHECK("scatter_rows_kernel");
     return PGLB_OK;
