@@ -116,9 +116,10 @@ int pglb_segment_indptr(const int64_t *segment_ids, int64_t num_edges, int64_t n
  *   scale_src[n_src] / scale_dst[n_dst] (nullable): msg *= scale_src[cols[j]] before the
  *   reduce, out[d] *= scale_dst[d] after it (GCNConv's two norm multiplies, conv.py:242,250)
  *   D = H * Dh output columns; head_dim = Dh (only used by PGLB_BCAST_HEAD).
- *   src_hot[n_src] (nullable, uint8): 1 = this source row is gathered often enough to be worth
- *   keeping in L2 (loaded with an evict_last policy, all other rows evict_first); a pure
- *   performance hint, results do not depend on it.  See pglb_hot_sources().
+ *   cols_packed[E] (nullable, uint32): a packed copy of cols made by pglb_pack_cols() (needs
+ *   n_src < 2^31).  Halves the index traffic of the wide-row kernel; with PGLB_SPMM_L2_HINTS in
+ *   flags, bit 31 marks sources worth keeping in L2 (evict_last, all other rows evict_first).
+ *   Pure performance hints: results do not depend on them.
  *   max_degree_hint : max row length if the caller knows it (skips the hub pass when
  *   small), or -1.
  * ---------------------------------------------------------------------------------- */
@@ -128,17 +129,19 @@ int pglb_spmm_csr_f32(const int64_t *indptr, const int64_t *cols, const int64_t 
                       float *out, int64_t ldo, int64_t n_dst, int64_t n_src,
                       int64_t num_edges, int64_t D, int64_t head_dim, int msg_op,
                       int reduce_op, const float *scale_src, const float *scale_dst,
-                      const uint8_t *src_hot, int64_t max_degree_hint, int flags, void *ws,
+                      const uint32_t *cols_packed, int64_t max_degree_hint, int flags, void *ws,
                       size_t ws_bytes, void *stream);
 /* flags of pglb_spmm_csr_f32 */
 #define PGLB_SPMM_ACCUMULATE 1 /* SUM only: out[d] = (out[d] + sum of messages) * scale_dst[d];
                                   lets a caller aggregate one edge subset while the feature rows of
                                   another subset (halo rows) are still in flight */
+#define PGLB_SPMM_L2_HINTS 2   /* bit 31 of cols_packed carries an L2 residency hint */
 
-/* L2 residency hint for pglb_spmm_csr_f32: counts how often every source occurs in cols[E]
- * (count[n_src], int32, zeroed by the call) and sets hot[i] = count[i] >= min_count. */
-int pglb_hot_sources(const int64_t *cols, int64_t num_edges, int64_t n_src, int32_t *count,
-                     int64_t min_count, uint8_t *hot, void *stream);
+/* Packed column ids for pglb_spmm_csr_f32: count[n_src] (int32, zeroed by the call) receives how
+ * often every source occurs in cols[E]; packed[j] = cols[j] | (count[cols[j]] >= min_count) << 31.
+ * Pass min_count = INT64_MAX for plain 32-bit ids without hints. */
+int pglb_pack_cols(const int64_t *cols, int64_t num_edges, int64_t n_src, int32_t *count,
+                   int64_t min_count, uint32_t *packed, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Edge-parallel ops

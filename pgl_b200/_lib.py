@@ -51,7 +51,7 @@ _SIGS = {
     "pglb_ipc_free": (c_int, [_p]),
     "pglb_ipc_open": (c_int, [_p, POINTER(c_void_p)]),
     "pglb_ipc_close": (c_int, [_p]),
-    "pglb_hot_sources": (c_int, [_p, _i64, _i64, _p, _i64, _p, _p]),
+    "pglb_pack_cols": (c_int, [_p, _i64, _i64, _p, _i64, _p, _p]),
     "pglb_send_uv_f32": (c_int, [_p, _p, _p, _i64, _p, _i64, _i64, _i64, c_int, _p, _p]),
     "pglb_gather_rows_f32": (c_int, [_p, _i64, _p, _i64, _i64, _i64, _p, _i64, _p]),
     "pglb_scatter_rows_f32": (c_int, [_p, _i64, _p, _i64, _i64, _p, _i64, _p]),

@@ -325,7 +325,7 @@ extern "C" int pglb_degree_norm_f32(const int64_t *degree, int64_t n, float *nor
     return PGLB_OK;
 }
 
-// ---- source hotness (L2 residency hint) ---------------------------------------------------
+// ---- packed column ids + source hotness (L2 residency hint) --------------------------------
 namespace pglb {
 __global__ void __launch_bounds__(256) col_count_kernel(const int64_t *__restrict__ cols, int64_t E,
                                                         int *__restrict__ count) {
@@ -333,26 +333,30 @@ __global__ void __launch_bounds__(256) col_count_kernel(const int64_t *__restric
          i += (int64_t)gridDim.x * blockDim.x)
         atomicAdd(count + __ldcs((const long long *)cols + i), 1);
 }
-__global__ void __launch_bounds__(256) hot_mask_kernel(const int *__restrict__ count, int64_t n,
-                                                       int64_t min_count, uint8_t *__restrict__ hot) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x)
-        hot[i] = count[i] >= min_count ? 1 : 0;
+__global__ void __launch_bounds__(256) pack_cols_kernel(const int64_t *__restrict__ cols, int64_t E,
+                                                        const int *__restrict__ count,
+                                                        int64_t min_count,
+                                                        uint32_t *__restrict__ packed) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = __ldcs((const long long *)cols + i);
+        const uint32_t hot = ((int64_t)__ldg(count + c) >= min_count) ? 0x80000000u : 0u;
+        packed[i] = (uint32_t)c | hot;
+    }
 }
 }  // namespace pglb
 
-extern "C" int pglb_hot_sources(const int64_t *cols, int64_t E, int64_t n_src, int32_t *count,
-                                int64_t min_count, uint8_t *hot, void *stream_) {
+extern "C" int pglb_pack_cols(const int64_t *cols, int64_t E, int64_t n_src, int32_t *count,
+                              int64_t min_count, uint32_t *packed, void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    PGLB_CHECK_ARG(E >= 0 && n_src >= 0, PGLB_EINVAL, "pglb_hot_sources: bad size");
-    if (n_src == 0) return PGLB_OK;
-    PGLB_CHECK_ARG(count && hot && (E == 0 || cols), PGLB_EINVAL, "pglb_hot_sources: NULL pointer");
+    PGLB_CHECK_ARG(E >= 0 && n_src >= 0, PGLB_EINVAL, "pglb_pack_cols: bad size");
+    PGLB_CHECK_ARG(n_src < 0x7fffffffLL, PGLB_ESHAPE, "pglb_pack_cols: needs n_src < 2^31");
+    if (n_src == 0 || E == 0) return PGLB_OK;
+    PGLB_CHECK_ARG(count && packed && cols, PGLB_EINVAL, "pglb_pack_cols: NULL pointer");
     PGLB_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t) * n_src, stream));
-    if (E > 0) {
-        col_count_kernel<<<grid_for(E), 256, 0, stream>>>(cols, E, count);
-        PGLB_LAUNCH_CHECK("col_count_kernel");
-    }
-    hot_mask_kernel<<<grid_for(n_src), 256, 0, stream>>>(count, n_src, min_count, hot);
-    PGLB_LAUNCH_CHECK("hot_mask_kernel");
+    col_count_kernel<<<grid_for(E), 256, 0, stream>>>(cols, E, count);
+    PGLB_LAUNCH_CHECK("col_count_kernel");
+    pack_cols_kernel<<<grid_for(E), 256, 0, stream>>>(cols, E, count, min_count, packed);
+    PGLB_LAUNCH_CHECK("pack_cols_kernel");
     return PGLB_OK;
 }

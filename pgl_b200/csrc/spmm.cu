@@ -417,8 +417,8 @@ size_t stream_ws_bytes(int64_t E, int64_t D);
 int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, int64_t ldx,
                     float *out, int64_t ldo, int64_t n_dst, int64_t n_src, int64_t E, int64_t D,
                     int reduce_op, const float *scale_src, const float *scale_dst,
-                    const uint8_t *src_hot, int accumulate, void *ws, size_t ws_bytes,
-                    cudaStream_t stream);
+                    const uint32_t *cols32, int l2_hints, int accumulate, void *ws,
+                    size_t ws_bytes, cudaStream_t stream);
 
 static bool use_stream_path() {
     static int v = -1;
@@ -448,7 +448,7 @@ extern "C" int pglb_spmm_csr_f32(const int64_t *indptr, const int64_t *cols, con
                                  int y_bcast, float *out, int64_t ldo, int64_t n_dst,
                                  int64_t n_src, int64_t num_edges, int64_t D, int64_t head_dim,
                                  int msg_op, int reduce_op, const float *scale_src,
-                                 const float *scale_dst, const uint8_t *src_hot,
+                                 const float *scale_dst, const uint32_t *cols_packed,
                                  int64_t max_degree_hint, int flags, void *ws, size_t ws_bytes,
                                  void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -483,8 +483,8 @@ extern "C" int pglb_spmm_csr_f32(const int64_t *indptr, const int64_t *cols, con
         PGLB_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255u) == 0, PGLB_EWORKSPACE,
                        "pglb_spmm_csr_f32: workspace must be 256-byte aligned");
         return spmm_stream_run(indptr, cols, x, ldx, out, ldo, n_dst, n_src, num_edges, D,
-                               reduce_op, scale_src, scale_dst, src_hot, accumulate, ws, ws_bytes,
-                               stream);
+                               reduce_op, scale_src, scale_dst, cols_packed,
+                               (flags & PGLB_SPMM_L2_HINTS) ? 1 : 0, accumulate, ws, ws_bytes, stream);
     }
     const Shape s = pick_shape(D, vec4);
     const int rk = (reduce_op >= PGLB_REDUCE_MAX) ? 1 : 0;

@@ -51,7 +51,7 @@ struct StreamP {
     float *partial;            // [2*ntasks, dpad]
     int64_t dpad;
     int64_t *tail_row;  // [ntasks]
-    const uint8_t *src_hot;  // nullable [n_src]: 1 = keep this source row in L2 (evict_last)
+    const uint32_t *cols32;  // nullable [E]: packed copy of cols, bit 31 = keep-in-L2 hint
     int accumulate;          // SUM only: out = (out_prev + sum) * scale_dst
     int hot_mode;            // 1: hot=evict_last cold=evict_first, 2: hot=last cold=normal, 3: hot=normal cold=first
 };
@@ -136,11 +136,13 @@ __global__ void __launch_bounds__(256) task_plan_kernel(const int64_t *__restric
 // ---------------------------------------------------------------------------------------------
 // D <= 128 (one float4 per lane per row)
 // ---------------------------------------------------------------------------------------------
-template <int RK, bool SCALED, bool HOT>
+template <int RK, bool SCALED, int PK>
 __global__ void __launch_bounds__(SW * 32, 2) spmm_stream128_kernel(const StreamP p) {
-    // HOT: bit 31 of the staged column id carries the source's L2 policy (hub sources that are
-    // gathered again and again are kept with evict_last, the long tail streams with evict_first
-    // so that it cannot flush them).
+    // PK 0: int64 column ids; 1: pre-packed uint32 ids (half the index bytes); 2: packed ids whose
+    // bit 31 carries the source's L2 policy (hub sources that are gathered again and again are
+    // kept with evict_last, the long tail streams through with evict_first so it cannot flush
+    // them).
+    constexpr bool HOT = (PK == 2);
     const uint64_t pol_last = !HOT ? 0 : (p.hot_mode == 3 ? policy_evict_normal() : policy_evict_last());
     const uint64_t pol_first = !HOT ? 0 : (p.hot_mode == 2 ? policy_evict_normal() : policy_evict_first());
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -209,9 +211,8 @@ __global__ void __launch_bounds__(SW * 32, 2) spmm_stream128_kernel(const Stream
         auto load_col = [&](int batch) -> unsigned {
             const int j = batch * 32 + lane;
             if (j >= cnt) return 0u;
-            unsigned c = (unsigned)(p.cols ? ld_stream(p.cols + a + j) : (a + j));
-            if (HOT) c |= (unsigned)__ldg(p.src_hot + c) << 31;
-            return c;
+            if (PK != 0) return __ldcs(p.cols32 + a + j);
+            return (unsigned)(p.cols ? ld_stream(p.cols + a + j) : (a + j));
         };
         // 32-bit column ids: the dispatcher routes n_src >= 2^32 to the generic kernel
         unsigned col_cur = load_col(0);
@@ -581,18 +582,18 @@ int64_t stream_task_size() {
 
 size_t stream_ws_bytes(int64_t E, int64_t D) { return stream_layout(nullptr, E, D, stream_task_size()).bytes; }
 
-template <int RK, bool SCALED, bool HOT>
+template <int RK, bool SCALED, int PK>
 static int launch_stream128(const StreamP &p, cudaStream_t stream) {
     const int smem = SW * RING * 512;
     static bool attr_set = false;
     if (!attr_set) {
-        PGLB_CUDA(cudaFuncSetAttribute(spmm_stream128_kernel<RK, SCALED, HOT>,
+        PGLB_CUDA(cudaFuncSetAttribute(spmm_stream128_kernel<RK, SCALED, PK>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     const int64_t blocks = (p.ntasks + SW - 1) / SW;
     PGLB_CHECK_ARG(blocks <= 0x7fffffffLL, PGLB_ESHAPE, "spmm_stream: grid too large");
-    spmm_stream128_kernel<RK, SCALED, HOT><<<(unsigned)blocks, SW * 32, smem, stream>>>(p);
+    spmm_stream128_kernel<RK, SCALED, PK><<<(unsigned)blocks, SW * 32, smem, stream>>>(p);
     PGLB_LAUNCH_CHECK("spmm_stream128_kernel");
     const int64_t fblocks = (p.ntasks * 32 + 255) / 256;
     spmm_stream_fixup_kernel<1, RK><<<(unsigned)fblocks, 256, 0, stream>>>(p);
@@ -625,8 +626,8 @@ static int launch_stream(const StreamP &p, int tiles, cudaStream_t stream) {
 int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, int64_t ldx,
                     float *out, int64_t ldo, int64_t n_dst, int64_t n_src, int64_t E, int64_t D,
                     int reduce_op, const float *scale_src, const float *scale_dst,
-                    const uint8_t *src_hot, int accumulate, void *ws, size_t ws_bytes,
-                    cudaStream_t stream) {
+                    const uint32_t *cols32, int l2_hints, int accumulate, void *ws,
+                    size_t ws_bytes, cudaStream_t stream) {
     const int64_t T = stream_task_size();
     PGLB_CHECK_ARG(E > 0, PGLB_EINVAL, "spmm_stream_run: needs at least one slot");
     StreamWs w = stream_layout(ws, E, D, T);
@@ -652,7 +653,7 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
     p.partial = w.partial;
     p.dpad = w.dpad;
     p.tail_row = w.tail_row;
-    p.src_hot = src_hot;
+    p.cols32 = cols32;
     p.accumulate = accumulate;
     {
         static int mode = 0;
@@ -673,14 +674,13 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
     const int rk = (reduce_op >= PGLB_REDUCE_MAX) ? 1 : 0;
     const bool small_ids = (cols ? n_src : E) < 0x7fffffffLL && ldx * 4 < 0xffffffffLL;
     if (cv <= 32 && small_ids) {
-        if (src_hot && cols) {
-            if (scale_src)
-                return rk ? launch_stream128<1, true, true>(p, stream) : launch_stream128<0, true, true>(p, stream);
-            return rk ? launch_stream128<1, false, true>(p, stream) : launch_stream128<0, false, true>(p, stream);
-        }
-        if (scale_src)
-            return rk ? launch_stream128<1, true, false>(p, stream) : launch_stream128<0, true, false>(p, stream);
-        return rk ? launch_stream128<1, false, false>(p, stream) : launch_stream128<0, false, false>(p, stream);
+        const int pk = (cols32 && cols) ? (l2_hints ? 2 : 1) : 0;
+#define PGLB_S128(RKV, SC)                                                         \
+    (pk == 2 ? launch_stream128<RKV, SC, 2>(p, stream)                             \
+             : pk == 1 ? launch_stream128<RKV, SC, 1>(p, stream) : launch_stream128<RKV, SC, 0>(p, stream))
+        if (scale_src) return rk ? PGLB_S128(1, true) : PGLB_S128(0, true);
+        return rk ? PGLB_S128(1, false) : PGLB_S128(0, false);
+#undef PGLB_S128
     }
     const int iters = cv <= 64 ? 2 : 4;
     const int tiles = (int)((cv + 32 * iters - 1) / (32 * iters));

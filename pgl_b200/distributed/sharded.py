@@ -183,7 +183,8 @@ class ShardedGraph(object):
     def _agg(self, csr, x_ext, reduce_op, scale_src, scale_dst, out=None, accumulate=False):
         return ops._spmm_raw(csr["indptr"], csr["cols"], x_ext, self.n_local, reduce_op,
                              scale_src=scale_src, scale_dst=scale_dst,
-                             max_degree=csr["max_degree"], out=out, accumulate=accumulate)
+                             max_degree=csr["max_degree"], out=out, accumulate=accumulate,
+                             packed=ops._packed_of(csr, x_ext))
 
     def send_recv(self, x_local, reduce_op="sum", scale_src=None, scale_dst=None):
         """Graph.send_recv on the shard: out rows = owned nodes."""

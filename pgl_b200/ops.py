@@ -127,7 +127,7 @@ def segment_indptr(segment_ids, num_segments):
 
 def _spmm_raw(indptr, cols, x2, n_dst, reduce_op, eid=None, y2=None, y_bcast=BCAST_FULL,
               head_dim=1, msg_op="copy", scale_src=None, scale_dst=None, max_degree=-1,
-              num_edges=None, out=None, src_hot=None, accumulate=False):
+              num_edges=None, out=None, packed=None, accumulate=False):
     dev = x2.device
     D = int(x2.shape[1])
     E = int(num_edges if num_edges is not None else (cols.shape[0] if cols is not None else 0))
@@ -142,8 +142,9 @@ def _spmm_raw(indptr, cols, x2, n_dst, reduce_op, eid=None, y2=None, y_bcast=BCA
             _ptr(indptr), _ptr(cols), _ptr(eid), _ptr(x2), x2.stride(0), _ptr(y2),
             (y2.stride(0) if y2 is not None else 0), y_bcast, _ptr(out), out.stride(0), n_dst,
             int(x2.shape[0]), E, D, head_dim, MSG[msg_op], REDUCE[reduce_op], _ptr(scale_src),
-            _ptr(scale_dst), _ptr(src_hot), int(max_degree), 1 if accumulate else 0, _ptr(ws), wsn,
-            _stream()))
+            _ptr(scale_dst), _ptr(packed[0]) if packed is not None else None, int(max_degree),
+            (1 if accumulate else 0) | (2 if (packed is not None and packed[1]) else 0), _ptr(ws),
+            wsn, _stream()))
     return out
 
 
@@ -200,27 +201,29 @@ def gather_rows_ptr(src_ptr, ld, index, out):
 HOT_L2_BYTES = int(float(os.environ.get("PGLB_HOT_MB", "0")) * (1 << 20))
 
 
-def hot_sources(cols, n_src, row_bytes, budget_bytes=None):
-    """uint8 mask of the sources worth pinning in L2 for an aggregation with `row_bytes` rows:
-    the most frequently gathered rows, as many as fit in `budget_bytes` (default PGLB_HOT_MB,
-    48 MB of the 126 MB L2).  None when the whole feature matrix fits the budget or the hint is
-    disabled (PGLB_HOT_MB=0).  One-off per graph; cached by EdgeIndex."""
+def pack_cols(cols, n_src, row_bytes, budget_bytes=None):
+    """(packed uint32 column ids, has_hints) for the wide-row aggregation kernel, or None when
+    ids do not fit 31 bits.  With a budget (PGLB_HOT_MB, default 0 = no hints) bit 31 marks the
+    most frequently gathered sources, as many as fit in the budget, for an evict_last L2 policy.
+    One-off per graph; cached by EdgeIndex."""
     budget = HOT_L2_BYTES if budget_bytes is None else int(budget_bytes)
     n_src = int(n_src)
     E = int(cols.shape[0])
-    k = budget // max(int(row_bytes), 1)
-    if budget <= 0 or k <= 0 or n_src <= k or n_src >= (1 << 31) or E == 0:
+    if n_src >= (1 << 31) - 1 or E == 0 or n_src == 0:
         return None
     dev = cols.device
     count = torch.empty(n_src, dtype=torch.int32, device=dev)
-    hot = torch.empty(n_src, dtype=torch.uint8, device=dev)
+    packed = torch.empty(E, dtype=torch.int32, device=dev)  # uint32 payload
+    k = budget // max(int(row_bytes), 1)
+    thr = (1 << 62)
+    hints = budget > 0 and 0 < k < n_src
+    if hints:
+        with torch.cuda.device(dev):
+            check(lib.pglb_pack_cols(_ptr(cols), E, n_src, _ptr(count), 1 << 62, _ptr(packed), _stream()))
+        thr = max(int(torch.topk(count, k, sorted=True).values[-1].item()), 2)
     with torch.cuda.device(dev):
-        check(lib.pglb_hot_sources(_ptr(cols), E, n_src, _ptr(count), 1 << 40, _ptr(hot), _stream()))
-    thr = int(torch.topk(count, k, sorted=True).values[-1].item())
-    thr = max(thr, 2)  # a row gathered once gains nothing from residency
-    with torch.cuda.device(dev):
-        check(lib.pglb_hot_sources(_ptr(cols), E, n_src, _ptr(count), thr, _ptr(hot), _stream()))
-    return hot
+        check(lib.pglb_pack_cols(_ptr(cols), E, n_src, _ptr(count), thr, _ptr(packed), _stream()))
+    return packed, hints
 
 
 class _CopyAgg(torch.autograd.Function):
@@ -236,7 +239,7 @@ class _CopyAgg(torch.autograd.Function):
         ctx.fwd = fwd
         return _spmm_raw(fwd["indptr"], fwd["cols"], x2, n_dst, reduce_op, scale_src=scale_src,
                          scale_dst=scale_dst, max_degree=fwd.get("max_degree", -1),
-                         src_hot=_hot_of(fwd, x2))
+                         packed=_packed_of(fwd, x2))
 
     @staticmethod
     def backward(ctx, g):
@@ -251,15 +254,16 @@ class _CopyAgg(torch.autograd.Function):
             s_in = inv if s_in is None else s_in * inv
         gx = _spmm_raw(bwd["indptr"], bwd["cols"], g, ctx.n_src, "sum", scale_src=s_in,
                        scale_dst=scale_src, max_degree=bwd.get("max_degree", -1),
-                       src_hot=_hot_of(bwd, g))
+                       packed=_packed_of(bwd, g))
         return gx, None, None, None, None, None, None
 
 
-def _hot_of(csr, x2):
-    """L2 residency hint for this (graph, row width), from the EdgeIndex cache."""
-    fn = csr.get("hot")
+def _packed_of(csr, x2):
+    """Packed column ids (+ optional L2 hints) for this (graph, row width), from the EdgeIndex
+    cache; only the wide-row kernel (64 < D <= 128) consumes them."""
+    fn = csr.get("packed")
     D = int(x2.shape[1])
-    if fn is None or D <= 64 or D > 128:
+    if fn is None or D <= 64 or D > 128 or D % 4:
         return None
     return fn(int(x2.shape[0]), D * 4)
 
@@ -274,7 +278,7 @@ def aggregate_copy(x, fwd, n_dst, reduce_op="sum", bwd=None, scale_src=None, sca
     else:
         out = _spmm_raw(fwd["indptr"], fwd["cols"], x2, n_dst, reduce_op, scale_src=scale_src,
                         scale_dst=scale_dst, max_degree=fwd.get("max_degree", -1),
-                        src_hot=_hot_of(fwd, x2))
+                        packed=_packed_of(fwd, x2))
     return out.reshape((n_dst,) + tuple(shape[1:]))
 
 

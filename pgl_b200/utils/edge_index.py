@@ -109,18 +109,18 @@ class EdgeIndex(object):
                 self._max_degree = int(np.max(self._degree))
         return self._max_degree
 
-    def hot_mask(self, n_src, row_bytes):
-        """Cached L2-residency hint (see ops.hot_sources) for gathers of `row_bytes` rows."""
-        cache = self.__dict__.setdefault("_hot_cache", {})
-        key = (int(n_src), int(row_bytes))
+    def packed_cols(self, n_src, row_bytes):
+        """Cached packed column ids (see ops.pack_cols) for gathers of `row_bytes` rows."""
+        cache = self.__dict__.setdefault("_packed_cache", {})
+        key = (int(n_src), int(row_bytes) if ops.HOT_L2_BYTES > 0 else 0)
         if key not in cache:
-            cache[key] = ops.hot_sources(self._sorted_v, n_src, row_bytes)
+            cache[key] = ops.pack_cols(self._sorted_v, n_src, row_bytes)
         return cache[key]
 
     def csr(self):
         """dict consumed by pgl_b200.ops: rows keyed by u, columns = v, eid per slot."""
         return {"indptr": self._indptr, "cols": self._sorted_v, "eid": self._sorted_eid,
-                "degree": self._degree, "max_degree": self.max_degree, "hot": self.hot_mask}
+                "degree": self._degree, "max_degree": self.max_degree, "packed": self.packed_cols}
 
     def view_v(self, u=None):
         """reference pgl/utils/edge_index.py:103-114 (numpy mode only)."""
