@@ -198,12 +198,12 @@ def gather_rows_ptr(src_ptr, ld, index, out):
     return out
 
 
-HOT_L2_BYTES = int(float(os.environ.get("PGLB_HOT_MB", "0")) * (1 << 20))
+HOT_L2_BYTES = int(float(os.environ.get("PGLB_HOT_MB", "32")) * (1 << 20))
 
 
 def pack_cols(cols, n_src, row_bytes, budget_bytes=None):
     """(packed uint32 column ids, has_hints) for the wide-row aggregation kernel, or None when
-    ids do not fit 31 bits.  With a budget (PGLB_HOT_MB, default 0 = no hints) bit 31 marks the
+    ids do not fit 31 bits.  With a budget (PGLB_HOT_MB, default 32 MB; 0 = no hints) bit 31 marks the
     most frequently gathered sources, as many as fit in the budget, for an evict_last L2 policy.
     One-off per graph; cached by EdgeIndex."""
     budget = HOT_L2_BYTES if budget_bytes is None else int(budget_bytes)
