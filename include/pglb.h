@@ -172,6 +172,28 @@ int pglb_edge_softmax_csr_f32(const int64_t *indptr, const int64_t *eid, const f
                               float *out, int64_t n_rows, int64_t num_edges, int64_t H,
                               void *ws, size_t ws_bytes, void *stream);
 
+/* ------------------------------------------------------------------------------------
+ * Backward kernels.  The reference gets every gradient from Paddle autograd through the ops
+ * above; sum / mean aggregation backward is pglb_spmm_csr_f32 on the reverse CSR, the rest:
+ * ---------------------------------------------------------------------------------- */
+/* out[e,h] = <a[ia[e],h,:], b[ib[e],h,:]>  (a, b rows of H*Dh floats; ia/ib strided like
+ * pglb_csr_build).  Gradient of send_ue_recv(mul) wrt the edge operand [E,H,1] (pgl/graph.py:930
+ * as used by GATConv, pgl/nn/conv.py:339) and of send_uv(mul). */
+int pglb_sddmm_dot_f32(const float *a, const float *b, const int64_t *ia, int64_t ia_stride,
+                       const int64_t *ib, int64_t ib_stride, int64_t num_edges, int64_t H,
+                       int64_t Dh, float *out, void *stream);
+/* gradient of pglb_edge_softmax_csr_f32: grad_logits = alpha * (grad - rowsum(alpha * grad)),
+ * same row / eid convention as the forward (pgl/math.py:216-224 differentiated). */
+int pglb_edge_softmax_bwd_csr_f32(const int64_t *indptr, const int64_t *eid, const float *alpha,
+                                  const float *grad, float *grad_logits, int64_t n_rows,
+                                  int64_t num_edges, int64_t H, void *stream);
+/* gradient of send_u_recv(max|min) wrt x on the reverse (src-keyed) CSR: every source entry that
+ * equals the reduced output receives the output's gradient (Paddle's send_u_recv grad contract).
+ *   src_indptr[n_src+1], dst_of_slot[E]; x [n_src, D], out / grad_out [n_dst, D], grad_x [n_src, D] */
+int pglb_maxmin_bwd_f32(const int64_t *src_indptr, const int64_t *dst_of_slot, const float *x,
+                        const float *out, const float *grad_out, float *grad_x, int64_t n_src,
+                        int64_t D, void *stream);
+
 /* norm[i] = clip(float(degree[i]), 1)^-0.5 ; GF.degree_norm (graph_op.py:46-55) */
 int pglb_degree_norm_f32(const int64_t *degree, int64_t n, float *norm, void *stream);
 

@@ -376,7 +376,8 @@ class Graph(object):
             "Only support 'sum', 'mean', 'max', 'min' built-in reduce functions."
         n_out = self._out_rows(feature, out_size)
         fwd = self._csr_for_rows(n_out)
-        return ops.aggregate_ue(feature, edge_feature, fwd, n_out, message_op, reduce_op)
+        return ops.aggregate_ue(feature, edge_feature, fwd, n_out, message_op, reduce_op,
+                                bwd=self._bwd_csr, edges=self._edges)
 
     def send_uv(self, src_feature, dst_feature, message_op="add"):
         """out[e] = x[src[e]] (op) y[dst[e]]; reference graph.py:939-966."""
@@ -385,7 +386,7 @@ class Graph(object):
         assert message_op in ["add", "sub", "mul", "div"], \
             "Only support 'add', 'sub', 'max', 'min' build-in message functions."
         return ops.send_uv(src_feature, dst_feature, self._edges[:, 0], self._edges[:, 1],
-                           message_op)
+                           message_op, src_csr=self._bwd_csr, dst_csr=self._fwd_csr)
 
     def send_ue(self, feature, edge_feature, message_op="add"):
         """reference graph.py:968-969."""

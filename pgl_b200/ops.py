@@ -258,6 +258,33 @@ class _CopyAgg(torch.autograd.Function):
         return gx, None, None, None, None, None, None
 
 
+class _MaxMinAgg(torch.autograd.Function):
+    """send_u_recv(max|min); backward routes the gradient to every source entry that equals the
+    reduced value (pglb_maxmin_bwd_f32 on the reverse CSR)."""
+
+    @staticmethod
+    def forward(ctx, x2, fwd, bwd, n_dst, reduce_op):
+        out = _spmm_raw(fwd["indptr"], fwd["cols"], x2, n_dst, reduce_op,
+                        max_degree=fwd.get("max_degree", -1), packed=_packed_of(fwd, x2))
+        ctx.bwd = bwd
+        ctx.save_for_backward(x2, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        bwd = ctx.bwd() if callable(ctx.bwd) else ctx.bwd
+        if bwd is None:
+            raise RuntimeError("pgl_b200: backward of this aggregation needs the reverse CSR")
+        x2, out = ctx.saved_tensors
+        g = g.contiguous()
+        gx = torch.empty_like(x2)
+        with torch.cuda.device(x2.device):
+            check(lib.pglb_maxmin_bwd_f32(_ptr(bwd["indptr"]), _ptr(bwd["cols"]), _ptr(x2), _ptr(out),
+                                          _ptr(g), _ptr(gx), int(x2.shape[0]), int(x2.shape[1]),
+                                          _stream()))
+        return gx, None, None, None, None
+
+
 def _packed_of(csr, x2):
     """Packed column ids (+ optional L2 hints) for this (graph, row width), from the EdgeIndex
     cache; only the wide-row kernel (64 < D <= 128) consumes them."""
@@ -273,8 +300,11 @@ def aggregate_copy(x, fwd, n_dst, reduce_op="sum", bwd=None, scale_src=None, sca
     require_cuda(x)
     shape = x.shape
     x2 = _f32_2d(x)
-    if reduce_op in ("sum", "mean") and x2.requires_grad and torch.is_grad_enabled():
+    needs_grad = x2.requires_grad and torch.is_grad_enabled()
+    if reduce_op in ("sum", "mean") and needs_grad:
         out = _CopyAgg.apply(x2, fwd, bwd, n_dst, reduce_op, scale_src, scale_dst)
+    elif needs_grad and scale_src is None and scale_dst is None:
+        out = _MaxMinAgg.apply(x2, fwd, bwd, n_dst, reduce_op)
     else:
         out = _spmm_raw(fwd["indptr"], fwd["cols"], x2, n_dst, reduce_op, scale_src=scale_src,
                         scale_dst=scale_dst, max_degree=fwd.get("max_degree", -1),
@@ -313,10 +343,68 @@ def classify_bcast(x_shape, y_shape):
     return None
 
 
-def aggregate_ue(x, y, fwd, n_dst, message_op="add", reduce_op="sum"):
+def sddmm_dot(a2, b2, ia, ib, H, Dh):
+    """out[e,h] = <a2[ia[e], h, :], b2[ib[e], h, :]>; a2, b2 are [n, H*Dh]."""
+    E = int(ia.shape[0])
+    out = torch.empty((E, H), dtype=torch.float32, device=a2.device)
+    with torch.cuda.device(a2.device):
+        check(lib.pglb_sddmm_dot_f32(_ptr(a2), _ptr(b2), _ptr(ia), max(ia.stride(0), 1) if E else 1,
+                                     _ptr(ib), max(ib.stride(0), 1) if E else 1, E, H, Dh, _ptr(out),
+                                     _stream()))
+    return out
+
+
+class _UeAgg(torch.autograd.Function):
+    """send_ue_recv with reduce sum and message mul / add, differentiable in x and y."""
+
+    @staticmethod
+    def forward(ctx, x2, y2, fwd, bwd, edges, n_dst, mode, hd, msg_op):
+        ctx.meta = (fwd, bwd, edges, mode, hd, msg_op)
+        ctx.save_for_backward(x2, y2)
+        return _spmm_raw(fwd["indptr"], fwd["cols"], x2, n_dst, "sum", eid=fwd["eid"], y2=y2,
+                         y_bcast=mode, head_dim=hd, msg_op=msg_op, max_degree=fwd.get("max_degree", -1))
+
+    @staticmethod
+    def backward(ctx, g):
+        fwd, bwd, edges, mode, hd, msg_op = ctx.meta
+        bwd = bwd() if callable(bwd) else bwd
+        x2, y2 = ctx.saved_tensors
+        g = g.contiguous()
+        n_src, D = int(x2.shape[0]), int(x2.shape[1])
+        src, dst = edges[:, 0], edges[:, 1]
+        gx = gy = None
+        if msg_op == "mul":
+            if ctx.needs_input_grad[0]:
+                gx = _spmm_raw(bwd["indptr"], bwd["cols"], g, n_src, "sum", eid=bwd["eid"], y2=y2,
+                               y_bcast=mode, head_dim=hd, msg_op="mul",
+                               max_degree=bwd.get("max_degree", -1))
+            if ctx.needs_input_grad[1]:
+                if mode == BCAST_FULL:
+                    gy = send_uv(x2, g, src, dst, "mul")
+                elif mode == BCAST_HEAD:
+                    gy = sddmm_dot(x2, g, src, dst, D // hd, hd)
+                else:
+                    gy = sddmm_dot(x2, g, src, dst, 1, D)
+        else:  # add
+            if ctx.needs_input_grad[0]:
+                gx = _spmm_raw(bwd["indptr"], bwd["cols"], g, n_src, "sum",
+                               max_degree=bwd.get("max_degree", -1))
+            if ctx.needs_input_grad[1]:
+                ge = gather_rows(g, dst)
+                if mode == BCAST_FULL:
+                    gy = ge
+                elif mode == BCAST_HEAD:
+                    gy = ge.reshape(ge.shape[0], D // hd, hd).sum(-1)
+                else:
+                    gy = ge.sum(-1, keepdim=True)
+        return gx, gy, None, None, None, None, None, None, None
+
+
+def aggregate_ue(x, y, fwd, n_dst, message_op="add", reduce_op="sum", bwd=None, edges=None):
     """send_ue_recv on a cached dst-CSR: y is in original edge order, read through eid."""
     require_cuda(x, y)
     xs = tuple(x.shape)
+    y_shape_in = tuple(y.shape)
     if y.dim() == 1:
         y = y.reshape(-1, 1)
     out_feat = torch.broadcast_shapes(tuple(x.shape[1:]) if x.dim() > 1 else (1,), tuple(y.shape[1:]))
@@ -330,9 +418,17 @@ def aggregate_ue(x, y, fwd, n_dst, message_op="add", reduce_op="sum"):
     mode, hd = cls
     x2 = _f32_2d(x)
     y2 = _f32_2d(y)
-    out = _spmm_raw(fwd["indptr"], fwd["cols"], x2, n_dst, reduce_op, eid=fwd["eid"], y2=y2,
-                    y_bcast=mode, head_dim=hd, msg_op=message_op,
-                    max_degree=fwd.get("max_degree", -1))
+    needs_grad = torch.is_grad_enabled() and (x2.requires_grad or y2.requires_grad)
+    if needs_grad:
+        if reduce_op != "sum" or message_op not in ("mul", "add") or bwd is None or edges is None:
+            raise NotImplementedError(
+                "pgl_b200: send_ue_recv is differentiable for message_op in (add, mul) with "
+                "reduce_op sum; got %s / %s" % (message_op, reduce_op))
+        out = _UeAgg.apply(x2, y2, fwd, bwd, edges, n_dst, mode, hd, message_op)
+    else:
+        out = _spmm_raw(fwd["indptr"], fwd["cols"], x2, n_dst, reduce_op, eid=fwd["eid"], y2=y2,
+                        y_bcast=mode, head_dim=hd, msg_op=message_op,
+                        max_degree=fwd.get("max_degree", -1))
     return out.reshape((n_dst,) + tuple(out_feat))
 
 
@@ -361,7 +457,56 @@ def segment_reduce(data, segment_ids, pool_type, num_segments=None, indptr=None,
 # ------------------------------------------------------------------------------------------
 
 
-def send_uv(x, y, src, dst, message_op="add"):
+def _send_uv_raw(x2, y2, src, dst, message_op):
+    E = int(src.shape[0])
+    D = int(x2.shape[1])
+    out = torch.empty((E, D), dtype=torch.float32, device=x2.device)
+    with torch.cuda.device(x2.device):
+        check(lib.pglb_send_uv_f32(_ptr(x2), _ptr(y2), _ptr(src), max(src.stride(0), 1) if E else 1,
+                                   _ptr(dst), max(dst.stride(0), 1) if E else 1, E, D,
+                                   MSG[message_op], _ptr(out), _stream()))
+    return out
+
+
+class _SendUV(torch.autograd.Function):
+    """send_uv (add / sub / mul) with gradients reduced over the cached src- and dst-CSR."""
+
+    @staticmethod
+    def forward(ctx, x2, y2, src, dst, message_op, src_csr, dst_csr):
+        ctx.meta = (message_op, src_csr, dst_csr)
+        ctx.save_for_backward(x2, y2)
+        return _send_uv_raw(x2, y2, src, dst, message_op)
+
+    @staticmethod
+    def backward(ctx, g):
+        op_, src_csr, dst_csr = ctx.meta
+        x2, y2 = ctx.saved_tensors
+        g = g.contiguous()
+        gx = gy = None
+        sc = src_csr() if callable(src_csr) else src_csr
+        dc = dst_csr() if callable(dst_csr) else dst_csr
+        if op_ in ("add", "sub"):
+            if ctx.needs_input_grad[0]:   # sum of g over the out-edges of every source
+                gx = _spmm_raw(sc["indptr"], sc["eid"], g, int(x2.shape[0]), "sum",
+                               max_degree=sc.get("max_degree", -1))
+            if ctx.needs_input_grad[1]:
+                gy = _spmm_raw(dc["indptr"], dc["eid"], g, int(y2.shape[0]), "sum",
+                               max_degree=dc.get("max_degree", -1))
+                if op_ == "sub":
+                    gy = -gy
+        elif op_ == "mul":
+            if ctx.needs_input_grad[0]:   # gx[s] = sum_e g[e] * y[dst[e]]
+                gx = _spmm_raw(sc["indptr"], sc["cols"], y2, int(x2.shape[0]), "sum", eid=sc["eid"],
+                               y2=g, y_bcast=BCAST_FULL, msg_op="mul", max_degree=sc.get("max_degree", -1))
+            if ctx.needs_input_grad[1]:
+                gy = _spmm_raw(dc["indptr"], dc["cols"], x2, int(y2.shape[0]), "sum", eid=dc["eid"],
+                               y2=g, y_bcast=BCAST_FULL, msg_op="mul", max_degree=dc.get("max_degree", -1))
+        else:
+            raise NotImplementedError("pgl_b200: send_uv(div) has no backward yet")
+        return gx, gy, None, None, None, None, None
+
+
+def send_uv(x, y, src, dst, message_op="add", src_csr=None, dst_csr=None):
     require_cuda(x, y, src, dst)
     xf = tuple(x.shape[1:]) if x.dim() > 1 else (1,)
     yf = tuple(y.shape[1:]) if y.dim() > 1 else (1,)
@@ -373,12 +518,10 @@ def send_uv(x, y, src, dst, message_op="add"):
     x2 = _f32_2d(x.reshape(x.shape[0], -1) if x.dim() != 2 else x)
     y2 = _f32_2d(y.reshape(y.shape[0], -1) if y.dim() != 2 else y)
     E = int(src.shape[0])
-    D = int(x2.shape[1])
-    out = torch.empty((E, D), dtype=torch.float32, device=x2.device)
-    with torch.cuda.device(x2.device):
-        check(lib.pglb_send_uv_f32(_ptr(x2), _ptr(y2), _ptr(src), max(src.stride(0), 1) if E else 1,
-                                   _ptr(dst), max(dst.stride(0), 1) if E else 1, E, D,
-                                   MSG[message_op], _ptr(out), _stream()))
+    if torch.is_grad_enabled() and (x2.requires_grad or y2.requires_grad) and src_csr is not None:
+        out = _SendUV.apply(x2, y2, src, dst, message_op, src_csr, dst_csr)
+    else:
+        out = _send_uv_raw(x2, y2, src, dst, message_op)
     return out.reshape((E,) + of)
 
 
@@ -420,14 +563,8 @@ def scatter_rows(init, index, updates):
     return out
 
 
-def edge_softmax_csr(indptr, eid, logits, num_edges):
-    """Fused per-row softmax; eid=None -> rows are contiguous slots (segment_softmax)."""
-    require_cuda(indptr, logits)
-    shape = logits.shape
-    l2 = logits.reshape(shape[0], -1) if logits.dim() != 2 else logits
-    l2 = _f32_2d(l2)
+def _edge_softmax_raw(indptr, eid, l2, E):
     H = int(l2.shape[1])
-    E = int(num_edges)
     out = torch.empty_like(l2)
     need = ctypes.c_size_t(0)
     check(lib.pglb_edge_softmax_csr_ws(E, ctypes.byref(need)))
@@ -436,6 +573,41 @@ def edge_softmax_csr(indptr, eid, logits, num_edges):
         check(lib.pglb_edge_softmax_csr_f32(_ptr(indptr), _ptr(eid), _ptr(l2), _ptr(out),
                                             int(indptr.shape[0]) - 1, E, H, _ptr(ws), ws.numel(),
                                             _stream()))
+    return out
+
+
+class _EdgeSoftmax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, l2, indptr, eid, E):
+        out = _edge_softmax_raw(indptr, eid, l2, E)
+        ctx.meta = (indptr, eid, E)
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        indptr, eid, E = ctx.meta
+        (alpha,) = ctx.saved_tensors
+        g = g.contiguous()
+        gl = torch.zeros_like(alpha)
+        with torch.cuda.device(alpha.device):
+            check(lib.pglb_edge_softmax_bwd_csr_f32(_ptr(indptr), _ptr(eid), _ptr(alpha), _ptr(g),
+                                                    _ptr(gl), int(indptr.shape[0]) - 1, E,
+                                                    int(alpha.shape[1]), _stream()))
+        return gl, None, None, None
+
+
+def edge_softmax_csr(indptr, eid, logits, num_edges):
+    """Fused per-row softmax; eid=None -> rows are contiguous slots (segment_softmax)."""
+    require_cuda(indptr, logits)
+    shape = logits.shape
+    l2 = logits.reshape(shape[0], -1) if logits.dim() != 2 else logits
+    l2 = _f32_2d(l2)
+    E = int(num_edges)
+    if l2.requires_grad and torch.is_grad_enabled():
+        out = _EdgeSoftmax.apply(l2, indptr, eid, E)
+    else:
+        out = _edge_softmax_raw(indptr, eid, l2, E)
     return out.reshape(shape)
 
 

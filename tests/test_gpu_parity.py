@@ -621,3 +621,102 @@ def test_cora_shaped_two_layer_gcn(pgl):
     loss = c2(g, c1(g, xt)).square().mean()
     loss.backward()
     assert xt.grad is not None and torch.isfinite(xt.grad).all() and c1.linear.weight.grad.abs().sum() > 0
+
+
+# ---------------------------------------------------------------- backward (vs torch fp32 autograd)
+def _torch_edge_softmax(logits, dst, n):
+    m = torch.full((n,) + logits.shape[1:], -float("inf"), device=logits.device)
+    m = m.scatter_reduce(0, dst.view(-1, *([1] * (logits.dim() - 1))).expand_as(logits), logits,
+                         "amax", include_self=True)
+    ex = torch.exp(logits - m[dst])
+    s = torch.zeros_like(m).index_add_(0, dst, ex)
+    return ex / s[dst]
+
+
+def test_backward_edge_softmax_send_uv_ue(pgl):
+    import pgl_b200.nn.functional as F
+    n, e, H, Dh = 600, 7000, 4, 8
+    edges = O.chung_lu_edges(n, e, exponent=0.8, seed=161)
+    g = make_graph(pgl, edges, n)
+    src, dst = dev(edges[:, 0]), dev(edges[:, 1])
+    torch.manual_seed(0)
+    # edge softmax
+    lg1 = torch.randn(e, H, device="cuda", requires_grad=True)
+    lg2 = lg1.detach().clone().requires_grad_(True)
+    go = torch.randn(e, H, device="cuda")
+    F.edge_softmax(g, lg1).backward(go)
+    _torch_edge_softmax(lg2, dst, n).backward(go)
+    assert rel_err(lg1.grad.cpu().numpy(), lg2.grad.cpu().numpy()) <= RTOL
+    # send_uv add / sub / mul
+    for mop in ("add", "sub", "mul"):
+        a1 = torch.randn(n, H, device="cuda", requires_grad=True)
+        b1 = torch.randn(n, H, device="cuda", requires_grad=True)
+        a2, b2 = a1.detach().clone().requires_grad_(True), b1.detach().clone().requires_grad_(True)
+        go = torch.randn(e, H, device="cuda")
+        g.send_uv(a1, b1, mop).backward(go)
+        ref = {"add": a2[src] + b2[dst], "sub": a2[src] - b2[dst], "mul": a2[src] * b2[dst]}[mop]
+        ref.backward(go)
+        assert rel_err(a1.grad.cpu().numpy(), a2.grad.cpu().numpy()) <= RTOL, mop
+        assert rel_err(b1.grad.cpu().numpy(), b2.grad.cpu().numpy()) <= RTOL, mop
+    # send_ue_recv mul (per-head, scalar, full) and add
+    for yshape, mop in (((e, H, 1), "mul"), ((e, 1, 1), "mul"), ((e, H, Dh), "mul"), ((e, H, 1), "add")):
+        x1 = torch.randn(n, H, Dh, device="cuda", requires_grad=True)
+        y1 = torch.randn(*yshape, device="cuda", requires_grad=True)
+        x2, y2 = x1.detach().clone().requires_grad_(True), y1.detach().clone().requires_grad_(True)
+        go = torch.randn(n, H, Dh, device="cuda")
+        g.send_ue_recv(x1, y1, mop, "sum").backward(go)
+        msg = x2[src] * y2 if mop == "mul" else x2[src] + y2
+        torch.zeros(n, H, Dh, device="cuda").index_add(0, dst, msg).backward(go)
+        assert rel_err(x1.grad.cpu().numpy(), x2.grad.cpu().numpy()) <= RTOL, (yshape, mop)
+        assert rel_err(y1.grad.cpu().numpy(), y2.grad.cpu().numpy()) <= RTOL, (yshape, mop)
+    with pytest.raises(NotImplementedError):
+        g.send_ue_recv(torch.randn(n, 4, device="cuda", requires_grad=True),
+                       torch.randn(e, 4, device="cuda"), "div", "sum")
+
+
+def test_backward_max_min(pgl):
+    n, e, d = 500, 6000, 24
+    edges = O.chung_lu_edges(n, e, exponent=0.8, seed=171)
+    g = make_graph(pgl, edges, n)
+    src, dst = dev(edges[:, 0]), dev(edges[:, 1])
+    for op_, red in (("max", "amax"), ("min", "amin")):
+        x1 = torch.randn(n, d, device="cuda", requires_grad=True)
+        x2 = x1.detach().clone().requires_grad_(True)
+        go = torch.randn(n, d, device="cuda")
+        g.send_recv(x1, op_).backward(go)
+        ref = torch.zeros(n, d, device="cuda").scatter_reduce(
+            0, dst.view(-1, 1).expand(e, d), x2[src], red, include_self=False)
+        ref.backward(go)
+        # duplicate edges tie exactly: Paddle's contract gives every tied entry the full gradient,
+        # torch splits it -- compare on the sum over tied duplicates instead: build from definition
+        out = ref.detach()
+        mask = (x2.detach()[src] == out[dst]).float()
+        want = torch.zeros(n, d, device="cuda").index_add_(0, src, go[dst] * mask)
+        assert rel_err(x1.grad.cpu().numpy(), want.cpu().numpy()) <= RTOL, op_
+
+
+def test_gat_conv_trains(pgl):
+    """GATConv forward + backward against a plain torch fp32 implementation of conv.py:308-346."""
+    n, e, H, Dh, fin = 400, 5000, 4, 8, 20
+    edges = O.chung_lu_edges(n, e, exponent=0.7, seed=181)
+    g = make_graph(pgl, edges, n)
+    src, dst = dev(edges[:, 0]), dev(edges[:, 1])
+    conv = pgl.nn.GATConv(fin, Dh, feat_drop=0, attn_drop=0, num_heads=H, concat=True).cuda()
+    x1 = torch.randn(n, fin, device="cuda", requires_grad=True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    go = torch.randn(n, H * Dh, device="cuda")
+    out = conv(g, x1)
+    out.backward(go)
+    grads = {k: p.grad.clone() for k, p in conv.named_parameters()}
+    conv.zero_grad()
+    f = (x2 @ conv.linear.weight + conv.linear.bias).reshape(-1, H, Dh)
+    a_s = (f * conv.weight_src).sum(-1)
+    a_d = (f * conv.weight_dst).sum(-1)
+    al = torch.nn.functional.leaky_relu(a_s[src] + a_d[dst], 0.2)
+    al = _torch_edge_softmax(al, dst, n)
+    ref = torch.zeros(n, H, Dh, device="cuda").index_add(0, dst, f[src] * al.unsqueeze(-1)).reshape(n, H * Dh)
+    ref.backward(go)
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= RTOL
+    assert rel_err(x1.grad.cpu().numpy(), x2.grad.cpu().numpy()) <= 5e-4
+    for k, p in conv.named_parameters():
+        assert rel_err(grads[k].cpu().numpy(), p.grad.cpu().numpy()) <= 5e-4, k
