@@ -34,6 +34,11 @@ def segment_pool(data, segment_ids, pool_type, name=None):
             "We only support sum, mean, max, min pool types in segment_pool function.")
     ops.require_cuda(data, segment_ids)
     indptr, maxdeg = _indptr_of(segment_ids)
+    from .utils.op import LazyRows
+    if isinstance(data, LazyRows) and data.is_lazy():
+        # untouched message rows: fuse the gather into the reduce (no [E, D] materialisation)
+        return ops.segment_reduce(data._lz_base, None, pool_type.lower(), indptr=indptr,
+                                  cols=data._lz_index.contiguous(), max_degree=maxdeg)
     return ops.segment_reduce(data, None, pool_type.lower(), indptr=indptr, max_degree=maxdeg)
 
 

@@ -432,6 +432,39 @@ def aggregate_ue(x, y, fwd, n_dst, message_op="add", reduce_op="sum", bwd=None, 
     return out.reshape((n_dst,) + tuple(out_feat))
 
 
+class _SegmentReduce(torch.autograd.Function):
+    """Row reduce over a compact CSR (segment_* / fused gather+segment).  Backward: sum / mean
+    expand the gradient back over the slots (then scatter-add through `cols` if the forward
+    gathered); max / min route it to the entries equal to the reduced value."""
+
+    @staticmethod
+    def forward(ctx, d2, indptr, cols, pool_type, max_degree, n_slots):
+        K = int(indptr.shape[0]) - 1
+        out = _spmm_raw(indptr, cols, d2, K, pool_type, num_edges=n_slots, max_degree=max_degree)
+        ctx.meta = (indptr, cols, pool_type, n_slots)
+        ctx.save_for_backward(d2, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        indptr, cols, pool_type, n_slots = ctx.meta
+        d2, out = ctx.saved_tensors
+        g = g.contiguous()
+        K = int(indptr.shape[0]) - 1
+        counts = indptr[1:] - indptr[:-1]
+        seg = torch.repeat_interleave(torch.arange(K, device=g.device), counts)  # slot -> row
+        ge = gather_rows(g, seg)  # [n_slots, D]
+        if pool_type == "mean":
+            ge = ge / counts.clamp(min=1).to(ge.dtype)[seg].unsqueeze(1)
+        elif pool_type in ("max", "min"):
+            src_rows = d2 if cols is None else gather_rows(d2, cols)
+            ge = ge * (src_rows == gather_rows(out, seg)).to(ge.dtype)
+        if cols is None:
+            return ge, None, None, None, None, None
+        gd = torch.zeros_like(d2).index_add_(0, cols, ge)
+        return gd, None, None, None, None, None
+
+
 def segment_reduce(data, segment_ids, pool_type, num_segments=None, indptr=None, cols=None,
                    max_degree=-1):
     """paddle.geometric.segment_* over sorted ids (reference pgl/math.py:36-42).
@@ -447,14 +480,13 @@ def segment_reduce(data, segment_ids, pool_type, num_segments=None, indptr=None,
     else:
         E = int(cols.shape[0]) if cols is not None else int(d2.shape[0])
         num_segments = int(indptr.shape[0]) - 1
-    out = _spmm_raw(indptr, cols, d2, int(num_segments), pool_type, num_edges=E,
-                    max_degree=max_degree)
-    return out.reshape((int(num_segments),) + tuple(data.shape[1:]))
-
-
-# ------------------------------------------------------------------------------------------
-# edge-parallel
-# ------------------------------------------------------------------------------------------
+    if d2.requires_grad and torch.is_grad_enabled():
+        out = _SegmentReduce.apply(d2, indptr, cols, pool_type, max_degree, E)
+    else:
+        out = _spmm_raw(indptr, cols, d2, int(num_segments), pool_type, num_edges=E,
+                        max_degree=max_degree)
+    feat = tuple(data.shape[1:])
+    return out.reshape((int(num_segments),) + feat)
 
 
 def _send_uv_raw(x2, y2, src, dst, message_op):
@@ -525,6 +557,33 @@ def send_uv(x, y, src, dst, message_op="add", src_csr=None, dst_csr=None):
     return out.reshape((E,) + of)
 
 
+def _gather_rows_raw(x2, index, out2=None):
+    n = int(index.shape[0])
+    D = int(x2.shape[1])
+    dev = index.device
+    if out2 is None:
+        out2 = torch.empty((n, D), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.pglb_gather_rows_f32(_ptr(x2), x2.stride(0), _ptr(index),
+                                       max(index.stride(0), 1) if n else 1, n, D, _ptr(out2),
+                                       out2.stride(0), _stream()))
+    return out2
+
+
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2, index):
+        ctx.meta = (index, int(x2.shape[0]))
+        return _gather_rows_raw(x2, index)
+
+    @staticmethod
+    def backward(ctx, g):
+        index, n = ctx.meta
+        gx = torch.zeros((n, g.shape[1]), dtype=g.dtype, device=g.device)
+        gx.index_add_(0, index.contiguous(), g.contiguous())
+        return gx, None
+
+
 def gather_rows(x, index, out=None):
     """paddle.gather(x, index, axis=0).  The kernel is launched on the device of ``index`` /
     ``out``; ``x`` may live on a peer GPU mapped into this process (NVLink P2P pull)."""
@@ -535,32 +594,45 @@ def gather_rows(x, index, out=None):
         return x.index_select(0, index.contiguous())  # integer gathers (degree subsets): torch device op
     x2 = _f32_2d(x)
     D = int(x2.shape[1])
-    dev = index.device
-    if out is None:
-        out2 = torch.empty((n, D), dtype=torch.float32, device=dev)
-    else:
+    if out is None and x2.requires_grad and torch.is_grad_enabled():
+        return _GatherRows.apply(x2, index).reshape((n,) + tuple(x.shape[1:]))
+    out2 = None
+    if out is not None:
         out2 = out.reshape(n, D) if out.dim() != 2 else out
-    with torch.cuda.device(dev):
-        check(lib.pglb_gather_rows_f32(_ptr(x2), x2.stride(0), _ptr(index),
-                                       max(index.stride(0), 1) if n else 1, n, D, _ptr(out2),
-                                       out2.stride(0), _stream()))
+    res = _gather_rows_raw(x2, index, out2)
     if out is not None:
         return out
-    return out2.reshape((n,) + tuple(x.shape[1:]))
+    return res.reshape((n,) + tuple(x.shape[1:]))
+
+
+class _ScatterRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, init, index, updates):
+        out = init.clone()
+        o2 = out.reshape(out.shape[0], -1) if out.dim() != 2 else out
+        u2 = _f32_2d(updates)
+        n = int(index.shape[0])
+        with torch.cuda.device(out.device):
+            check(lib.pglb_scatter_rows_f32(_ptr(u2), u2.stride(0), _ptr(index), n, int(u2.shape[1]),
+                                            _ptr(o2), o2.stride(0), _stream()))
+        ctx.index = index
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        index = ctx.index
+        g = g.contiguous()
+        gu = _gather_rows_raw(g.reshape(g.shape[0], -1), index).reshape((index.shape[0],) + tuple(g.shape[1:]))
+        gi = g.clone()
+        gi.index_fill_(0, index, 0)
+        return gi, None, gu
 
 
 def scatter_rows(init, index, updates):
     """paddle.scatter(init, index, updates, overwrite=True) for unique indices (out-of-place)."""
     require_cuda(init, index, updates)
-    out = init.clone()
-    o2 = out.reshape(out.shape[0], -1) if out.dim() != 2 else out
-    u2 = _f32_2d(updates)
     index = _i64(index).contiguous()
-    n = int(index.shape[0])
-    with torch.cuda.device(out.device):
-        check(lib.pglb_scatter_rows_f32(_ptr(u2), u2.stride(0), _ptr(index), n, int(u2.shape[1]),
-                                        _ptr(o2), o2.stride(0), _stream()))
-    return out
+    return _ScatterRows.apply(init, index, updates)
 
 
 def _edge_softmax_raw(indptr, eid, l2, E):
