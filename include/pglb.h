@@ -197,6 +197,14 @@ int pglb_maxmin_bwd_f32(const int64_t *src_indptr, const int64_t *dst_of_slot, c
 /* norm[i] = clip(float(degree[i]), 1)^-0.5 ; GF.degree_norm (graph_op.py:46-55) */
 int pglb_degree_norm_f32(const int64_t *degree, int64_t n, float *norm, void *stream);
 
+/* Strided host<->device copy on `stream` (cudaMemcpy2DAsync): moves a column block of a row-major
+ * matrix without staging.  kind: 1 = host->device, 2 = device->host.  Used by the host-buffer
+ * entry of the aggregation (features in pinned host memory): column chunks are independent for a
+ * copy-message aggregation, so chunk c+1's upload, chunk c's kernel and chunk c-1's download
+ * overlap (PCIe is full duplex). */
+int pglb_memcpy2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_pitch,
+                        size_t width_bytes, size_t height, int kind, void *stream);
+
 /* ------------------------------------------------------------------------------------
  * Peer-mappable device buffers for the multi-GPU halo pull (NVLink P2P, one process per GPU).
  * The only place the library allocates: cudaMalloc'ed buffers whose CUDA IPC handle (64 bytes)

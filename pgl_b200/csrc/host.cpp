@@ -67,6 +67,18 @@ extern "C" int pglb_build_index_host(const int64_t *u, int64_t us, const int64_t
     return PGLB_OK;
 }
 
+extern "C" int pglb_memcpy2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_pitch,
+                                   size_t width_bytes, size_t height, int kind, void *stream) {
+    if (width_bytes == 0 || height == 0) return PGLB_OK;
+    if (!dst || !src || (kind != 1 && kind != 2) || dst_pitch < width_bytes || src_pitch < width_bytes)
+        return fail(PGLB_EINVAL, "pglb_memcpy2d_async: bad args");
+    cudaError_t e = cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, height,
+                                      kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                                      reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy2DAsync");
+    return PGLB_OK;
+}
+
 // ---- peer-mappable buffers (CUDA IPC) ---------------------------------------------------------
 extern "C" int pglb_ipc_alloc(size_t bytes, void **dev_ptr, void *handle64) {
     if (!dev_ptr || !handle64 || bytes == 0) return fail(PGLB_EINVAL, "pglb_ipc_alloc: bad args");

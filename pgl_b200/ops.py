@@ -148,6 +148,62 @@ def _spmm_raw(indptr, cols, x2, n_dst, reduce_op, eid=None, y2=None, y_bcast=BCA
     return out
 
 
+class HostAggregator(object):
+    """send_u_recv for features that live in (pinned) HOST memory: out_host = aggregate(x_host).
+
+    The graph stays resident on the GPU; per call the [N, D] float32 matrix is streamed through
+    the GPU in `chunks` column blocks on three streams -- upload of block c+1, aggregation of block
+    c and download of block c-1 run concurrently (PCIe is full duplex, and the columns of a
+    copy-message aggregation are independent) -- so a call costs about one direction of PCIe
+    traffic instead of two plus the kernel."""
+
+    def __init__(self, fwd, n_src, n_dst, dim, device, chunks=4):
+        self.fwd, self.n_src, self.n_dst, self.dim = fwd, int(n_src), int(n_dst), int(dim)
+        self.device = device
+        chunks = max(1, min(int(chunks), self.dim // 4 if self.dim >= 4 else 1))
+        w = -(-self.dim // chunks)
+        w = (w + 3) // 4 * 4
+        self.bounds = [(c, min(c + w, self.dim)) for c in range(0, self.dim, w)]
+        self.xd = torch.empty((self.n_src, self.dim), dtype=torch.float32, device=device)
+        self.od = torch.empty((self.n_dst, self.dim), dtype=torch.float32, device=device)
+        self.s_in = torch.cuda.Stream(device=device)
+        self.s_out = torch.cuda.Stream(device=device)
+
+    def __call__(self, x_host, out_host, reduce_op="sum", scale_src=None, scale_dst=None):
+        assert x_host.dtype == torch.float32 and out_host.dtype == torch.float32
+        assert tuple(x_host.shape) == (self.n_src, self.dim) and x_host.is_contiguous()
+        assert tuple(out_host.shape) == (self.n_dst, self.dim) and out_host.is_contiguous()
+        main = torch.cuda.current_stream(self.device)
+        self.s_in.wait_stream(main)
+        self.s_out.wait_stream(main)
+        pitch = self.dim * 4
+        ev_in, ev_done = [], []
+        with torch.cuda.device(self.device):
+            for lo, hi in self.bounds:
+                check(lib.pglb_memcpy2d_async(
+                    ctypes.c_void_p(self.xd.data_ptr() + lo * 4), pitch,
+                    ctypes.c_void_p(x_host.data_ptr() + lo * 4), pitch, (hi - lo) * 4, self.n_src, 1,
+                    ctypes.c_void_p(self.s_in.cuda_stream)))
+                e = torch.cuda.Event()
+                e.record(self.s_in)
+                ev_in.append(e)
+            for i, (lo, hi) in enumerate(self.bounds):
+                main.wait_event(ev_in[i])
+                _spmm_raw(self.fwd["indptr"], self.fwd["cols"], self.xd[:, lo:hi], self.n_dst, reduce_op,
+                          scale_src=scale_src, scale_dst=scale_dst,
+                          max_degree=self.fwd.get("max_degree", -1), out=self.od[:, lo:hi],
+                          packed=_packed_of(self.fwd, self.xd[:, lo:hi]))
+                e = torch.cuda.Event()
+                e.record(main)
+                self.s_out.wait_event(e)
+                check(lib.pglb_memcpy2d_async(
+                    ctypes.c_void_p(out_host.data_ptr() + lo * 4), pitch,
+                    ctypes.c_void_p(self.od.data_ptr() + lo * 4), pitch, (hi - lo) * 4, self.n_dst, 2,
+                    ctypes.c_void_p(self.s_out.cuda_stream)))
+        main.wait_stream(self.s_out)
+        return out_host
+
+
 class IpcBuffer(object):
     """A cudaMalloc'ed float32 [rows, cols] buffer with a CUDA IPC handle (pglb_ipc_alloc), exposed
     to torch zero-copy through __cuda_array_interface__.  Used for the multi-GPU feature buffer

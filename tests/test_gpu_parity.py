@@ -773,3 +773,23 @@ def test_udf_path_backward(pgl):
         ref.backward(go)
         assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= RTOL
         assert rel_err(x1.grad.cpu().numpy(), x2.grad.cpu().numpy()) <= RTOL, fused
+
+
+def test_send_recv_host_pipelined(pgl):
+    """Host-buffer entry: column-chunked upload / aggregate / download == resident result."""
+    n, e, d = 30000, 400000, 128
+    edges = O.chung_lu_edges(n, e, exponent=0.9, seed=211)
+    g = make_graph(pgl, edges, n)
+    x = torch.randn(n, d)
+    xh = x.pin_memory()
+    norm = torch.rand(n, device="cuda") + 0.5
+    ref = g._send_u_recv(x.cuda(), "sum", None, scale_src=norm, scale_dst=norm)
+    for chunks in (1, 2, 4, 5):
+        oh = torch.empty(n, d).pin_memory()
+        g.send_recv_host(xh, oh, "sum", scale_src=norm, scale_dst=norm, chunks=chunks)
+        torch.cuda.synchronize()
+        assert rel_err(oh.numpy(), ref.cpu().numpy()) <= RTOL, chunks
+    oh = g.send_recv_host(xh, None, "mean")
+    torch.cuda.synchronize()
+    want = O.send_u_recv(x.numpy(), edges[:, 0], edges[:, 1], "mean")
+    assert rel_err(oh.numpy(), want) <= RTOL
