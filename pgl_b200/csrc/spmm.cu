@@ -417,7 +417,8 @@ size_t stream_ws_bytes(int64_t E, int64_t D);
 int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, int64_t ldx,
                     float *out, int64_t ldo, int64_t n_dst, int64_t n_src, int64_t E, int64_t D,
                     int reduce_op, const float *scale_src, const float *scale_dst,
-                    const uint32_t *cols32, int l2_hints, int accumulate, void *ws,
+                    const uint32_t *cols32, int l2_hints, int accumulate, const int64_t *eid,
+                    const float *y, int64_t ldy, int y_bcast, int head_dim, int msg_op, void *ws,
                     size_t ws_bytes, cudaStream_t stream);
 
 static bool use_stream_path() {
@@ -479,12 +480,19 @@ extern "C" int pglb_spmm_csr_f32(const int64_t *indptr, const int64_t *cols, con
     const bool vec4 = (D % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) && aligned16(x) &&
                       aligned16(out) &&
                       (mode == 0 || y_bcast != PGLB_BCAST_FULL || ((ldy % 4 == 0) && aligned16(y)));
-    if (mode == 0 && vec4 && D > 64 && num_edges > 0 && use_stream_path()) {
+    // wide rows: the edge-balanced cp.async-ring kernels (spmm_stream.cu).  With an edge operand
+    // only the GAT shape qualifies: per-head (head_dim % 4 == 0) or scalar y, mul / add, D <= 128.
+    const bool ue_fast = mode == 1 && D <= 128 && scale_src == nullptr && num_edges < 0x7fffffffLL &&
+                         (msg_op == PGLB_MSG_MUL || msg_op == PGLB_MSG_ADD) &&
+                         (y_bcast == PGLB_BCAST_SCALAR || (y_bcast == PGLB_BCAST_HEAD && head_dim % 4 == 0));
+    if ((mode == 0 || ue_fast) && vec4 && D > 64 && num_edges > 0 && use_stream_path()) {
         PGLB_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255u) == 0, PGLB_EWORKSPACE,
                        "pglb_spmm_csr_f32: workspace must be 256-byte aligned");
         return spmm_stream_run(indptr, cols, x, ldx, out, ldo, n_dst, n_src, num_edges, D,
-                               reduce_op, scale_src, scale_dst, cols_packed,
-                               (flags & PGLB_SPMM_L2_HINTS) ? 1 : 0, accumulate, ws, ws_bytes, stream);
+                               reduce_op, scale_src, scale_dst, mode == 0 ? cols_packed : nullptr,
+                               (flags & PGLB_SPMM_L2_HINTS) ? 1 : 0, accumulate, eid,
+                               mode == 1 ? y : nullptr, ldy, y_bcast, (int)head_dim, msg_op, ws,
+                               ws_bytes, stream);
     }
     const Shape s = pick_shape(D, vec4);
     const int rk = (reduce_op >= PGLB_REDUCE_MAX) ? 1 : 0;

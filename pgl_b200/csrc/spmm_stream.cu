@@ -52,6 +52,12 @@ struct StreamP {
     int64_t dpad;
     int64_t *tail_row;  // [ntasks]
     const uint32_t *cols32;  // nullable [E]: packed copy of cols, bit 31 = keep-in-L2 hint
+    const int64_t *eid;      // nullable: edge id per slot (row of y); identity if NULL
+    const float *y;          // nullable: edge operand (send_ue_recv), one scalar per lane per edge
+    int64_t ldy;
+    int y_bcast;             // PGLB_BCAST_HEAD or PGLB_BCAST_SCALAR
+    int head_dim;
+    int msg_op;              // PGLB_MSG_MUL or PGLB_MSG_ADD
     int accumulate;          // SUM only: out = (out_prev + sum) * scale_dst
     int hot_mode;            // 1: hot=evict_last cold=evict_first, 2: hot=last cold=normal, 3: hot=normal cold=first
 };
@@ -78,6 +84,14 @@ __device__ __forceinline__ uint64_t policy_evict_normal() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;\n" : "=l"(p));
     return p;
+}
+__device__ __forceinline__ void cp_async4(unsigned smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ float lds32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -136,8 +150,14 @@ __global__ void __launch_bounds__(256) task_plan_kernel(const int64_t *__restric
 // ---------------------------------------------------------------------------------------------
 // D <= 128 (one float4 per lane per row)
 // ---------------------------------------------------------------------------------------------
-template <int RK, bool SCALED, int PK>
-__global__ void __launch_bounds__(SW * 32, 2) spmm_stream128_kernel(const StreamP p) {
+constexpr int SWY = 5;  // warps per block when an edge operand is staged too (5 * 20 KB)
+
+template <int RK, bool SCALED, int PK, int YM>
+__global__ void __launch_bounds__((YM ? SWY : SW) * 32, 2) spmm_stream128_kernel(const StreamP p) {
+    // YM 1: message = x[src] (mul|add) y[eid, head(lane)] (send_ue_recv with a per-head or scalar
+    // edge operand, the GAT aggregation): the 4-byte operand of every edge rides in a second
+    // per-lane ring, fetched with cp.async alongside the feature row.
+    constexpr int W = YM ? SWY : SW;
     // PK 0: int64 column ids; 1: pre-packed uint32 ids (half the index bytes); 2: packed ids whose
     // bit 31 carries the source's L2 policy (hub sources that are gathered again and again are
     // kept with evict_last, the long tail streams through with evict_first so it cannot flush
@@ -148,9 +168,13 @@ __global__ void __launch_bounds__(SW * 32, 2) spmm_stream128_kernel(const Stream
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const int64_t task = (int64_t)blockIdx.x * SW + wib;
+    const int64_t task = (int64_t)blockIdx.x * W + wib;
     if (task >= p.ntasks) return;
-    const unsigned ring = (unsigned)__cvta_generic_to_shared(smem_raw) + wib * (RING * 512) + lane * 16;
+    const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned ring = smem0 + wib * (RING * 512) + lane * 16;
+    const unsigned ring2 = smem0 + W * (RING * 512) + wib * (RING * 128) + lane * 4;
+    const float *ylane = nullptr;
+    if (YM) ylane = p.y + ((p.y_bcast == PGLB_BCAST_HEAD) ? (lane * 4) / p.head_dim : 0);
 
     const bool is_max = (p.reduce_op == PGLB_REDUCE_MAX);
     const float ident = (RK == 0) ? 0.0f : (is_max ? -INFINITY : INFINITY);
@@ -214,9 +238,16 @@ __global__ void __launch_bounds__(SW * 32, 2) spmm_stream128_kernel(const Stream
             if (PK != 0) return __ldcs(p.cols32 + a + j);
             return (unsigned)(p.cols ? ld_stream(p.cols + a + j) : (a + j));
         };
+        auto load_eid = [&](int batch) -> unsigned {
+            const int j = batch * 32 + lane;
+            if (!YM || j >= cnt) return 0u;
+            return (unsigned)(p.eid ? ld_stream(p.eid + a + j) : (a + j));
+        };
         // 32-bit column ids: the dispatcher routes n_src >= 2^32 to the generic kernel
         unsigned col_cur = load_col(0);
         unsigned col_nxt = load_col(1);
+        unsigned eid_cur = load_eid(0);
+        unsigned eid_nxt = load_eid(1);
         float sc_cur = 1.0f, sc_prev = 1.0f;
         if (SCALED) sc_cur = (lane < cnt) ? __ldg(p.scale_src + (col_cur & 0x7fffffffu)) : 1.0f;
 
@@ -234,6 +265,10 @@ __global__ void __launch_bounds__(SW * 32, 2) spmm_stream128_kernel(const Stream
                     sc_prev = sc_cur;
                     col_cur = col_nxt;
                     col_nxt = load_col((g >> 2) + 1);
+                    if (YM) {
+                        eid_cur = eid_nxt;
+                        eid_nxt = load_eid((g >> 2) + 1);
+                    }
                     if (SCALED)
                         sc_cur = (base + lane < cnt) ? __ldg(p.scale_src + (col_cur & 0x7fffffffu)) : 1.0f;
                 }
@@ -242,6 +277,11 @@ __global__ void __launch_bounds__(SW * 32, 2) spmm_stream128_kernel(const Stream
 #pragma unroll
                 for (int k = 0; k < GRP; ++k) {
                     const unsigned c = __shfl_sync(0xffffffffu, col_cur, sub * GRP + k);
+                    if (YM) {
+                        const unsigned eidk = __shfl_sync(0xffffffffu, eid_cur, sub * GRP + k);
+                        if (k < valid)
+                            cp_async4(ring2 + (sub * GRP + k) * 128, ylane + (size_t)eidk * p.ldy);
+                    }
                     if (k < valid) {
                         if (HOT) {
                             const uint64_t pol = (c >> 31) ? pol_last : pol_first;
@@ -271,7 +311,17 @@ __global__ void __launch_bounds__(SW * 32, 2) spmm_stream128_kernel(const Stream
                         finish_row();
                         k_end = end_rel - base;
                     }
-                    const float4 v = lds128(gaddr + k * 512);
+                    float4 v = lds128(gaddr + k * 512);
+                    if (YM) {
+                        const float yv = lds32(ring2 + (csub * GRP + k) * 128);
+                        if (p.msg_op == PGLB_MSG_MUL) {
+                            v.x = __fmul_rn(v.x, yv); v.y = __fmul_rn(v.y, yv);
+                            v.z = __fmul_rn(v.z, yv); v.w = __fmul_rn(v.w, yv);
+                        } else {
+                            v.x = __fadd_rn(v.x, yv); v.y = __fadd_rn(v.y, yv);
+                            v.z = __fadd_rn(v.z, yv); v.w = __fadd_rn(v.w, yv);
+                        }
+                    }
                     float s = 1.0f;
                     if (SCALED) s = __shfl_sync(0xffffffffu, sc_reg, csub * GRP + k);
                     if (RK == 0) {
@@ -582,18 +632,19 @@ int64_t stream_task_size() {
 
 size_t stream_ws_bytes(int64_t E, int64_t D) { return stream_layout(nullptr, E, D, stream_task_size()).bytes; }
 
-template <int RK, bool SCALED, int PK>
+template <int RK, bool SCALED, int PK, int YM>
 static int launch_stream128(const StreamP &p, cudaStream_t stream) {
-    const int smem = SW * RING * 512;
+    constexpr int W = YM ? SWY : SW;
+    const int smem = W * RING * (512 + (YM ? 128 : 0));
     static bool attr_set = false;
     if (!attr_set) {
-        PGLB_CUDA(cudaFuncSetAttribute(spmm_stream128_kernel<RK, SCALED, PK>,
+        PGLB_CUDA(cudaFuncSetAttribute(spmm_stream128_kernel<RK, SCALED, PK, YM>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    const int64_t blocks = (p.ntasks + SW - 1) / SW;
+    const int64_t blocks = (p.ntasks + W - 1) / W;
     PGLB_CHECK_ARG(blocks <= 0x7fffffffLL, PGLB_ESHAPE, "spmm_stream: grid too large");
-    spmm_stream128_kernel<RK, SCALED, PK><<<(unsigned)blocks, SW * 32, smem, stream>>>(p);
+    spmm_stream128_kernel<RK, SCALED, PK, YM><<<(unsigned)blocks, W * 32, smem, stream>>>(p);
     PGLB_LAUNCH_CHECK("spmm_stream128_kernel");
     const int64_t fblocks = (p.ntasks * 32 + 255) / 256;
     spmm_stream_fixup_kernel<1, RK><<<(unsigned)fblocks, 256, 0, stream>>>(p);
@@ -626,7 +677,8 @@ static int launch_stream(const StreamP &p, int tiles, cudaStream_t stream) {
 int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, int64_t ldx,
                     float *out, int64_t ldo, int64_t n_dst, int64_t n_src, int64_t E, int64_t D,
                     int reduce_op, const float *scale_src, const float *scale_dst,
-                    const uint32_t *cols32, int l2_hints, int accumulate, void *ws,
+                    const uint32_t *cols32, int l2_hints, int accumulate, const int64_t *eid,
+                    const float *y, int64_t ldy, int y_bcast, int head_dim, int msg_op, void *ws,
                     size_t ws_bytes, cudaStream_t stream) {
     const int64_t T = stream_task_size();
     PGLB_CHECK_ARG(E > 0, PGLB_EINVAL, "spmm_stream_run: needs at least one slot");
@@ -654,6 +706,12 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
     p.dpad = w.dpad;
     p.tail_row = w.tail_row;
     p.cols32 = cols32;
+    p.eid = eid;
+    p.y = y;
+    p.ldy = ldy;
+    p.y_bcast = y_bcast;
+    p.head_dim = head_dim > 0 ? head_dim : 1;
+    p.msg_op = msg_op;
     p.accumulate = accumulate;
     {
         static int mode = 0;
@@ -674,10 +732,13 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
     const int rk = (reduce_op >= PGLB_REDUCE_MAX) ? 1 : 0;
     const bool small_ids = (cols ? n_src : E) < 0x7fffffffLL && ldx * 4 < 0xffffffffLL;
     if (cv <= 32 && small_ids) {
+        if (y) {  // edge operand: plain int64 ids, no source scale
+            return rk ? launch_stream128<1, false, 0, 1>(p, stream) : launch_stream128<0, false, 0, 1>(p, stream);
+        }
         const int pk = (cols32 && cols) ? (l2_hints ? 2 : 1) : 0;
 #define PGLB_S128(RKV, SC)                                                         \
-    (pk == 2 ? launch_stream128<RKV, SC, 2>(p, stream)                             \
-             : pk == 1 ? launch_stream128<RKV, SC, 1>(p, stream) : launch_stream128<RKV, SC, 0>(p, stream))
+    (pk == 2 ? launch_stream128<RKV, SC, 2, 0>(p, stream)                          \
+             : pk == 1 ? launch_stream128<RKV, SC, 1, 0>(p, stream) : launch_stream128<RKV, SC, 0, 0>(p, stream))
         if (scale_src) return rk ? PGLB_S128(1, true) : PGLB_S128(0, true);
         return rk ? PGLB_S128(1, false) : PGLB_S128(0, false);
 #undef PGLB_S128

@@ -793,3 +793,28 @@ def test_send_recv_host_pipelined(pgl):
     torch.cuda.synchronize()
     want = O.send_u_recv(x.numpy(), edges[:, 0], edges[:, 1], "mean")
     assert rel_err(oh.numpy(), want) <= RTOL
+
+
+@pytest.mark.parametrize("rop", ["sum", "mean", "max", "min"])
+def test_send_ue_recv_wide_rows_gat_shape(pgl, rop):
+    """x [N,8,16] with a per-head / scalar edge operand: the cp.async-ring kernel with the second
+    (edge operand) ring; hubs included."""
+    n, e, H, Dh = 4000, 90000, 8, 16
+    edges = O.chung_lu_edges(n, e, exponent=0.9, seed=221)
+    rng = np.random.default_rng(222)
+    x = rng.standard_normal((n, H, Dh)).astype(np.float32)
+    g = make_graph(pgl, edges, n)
+    for yshape, mop in (((e, H, 1), "mul"), ((e, H, 1), "add"), ((e, 1, 1), "mul")):
+        y = (rng.random(yshape).astype(np.float32) + 0.5)
+        out = g.send_ue_recv(dev(x), dev(y), mop, rop).cpu().numpy()
+        want = O.send_ue_recv(x, y, edges[:, 0], edges[:, 1], mop, rop)
+        assert out.shape == want.shape
+        if rop in ("max", "min"):
+            np.testing.assert_array_equal(out, want)
+        else:
+            check(out, want, g.adj_dst_index.max_degree)
+    # D = 100 (25 active lanes), Dh = 20
+    x2 = rng.standard_normal((n, 5, 20)).astype(np.float32)
+    y2 = rng.random((e, 5, 1)).astype(np.float32)
+    out = g.send_ue_recv(dev(x2), dev(y2), "mul", rop).cpu().numpy()
+    assert rel_err(out, O.send_ue_recv(x2, y2, edges[:, 0], edges[:, 1], "mul", rop)) <= RTOL
