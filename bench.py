@@ -377,7 +377,7 @@ def main_ours(args):
             x_host = torch.empty((n, d), dtype=torch.float32, pin_memory=True)
             x_host.copy_(x)
             out_host = torch.empty((n, d), dtype=torch.float32, pin_memory=True)
-            chunks = int(os.environ.get("PGLB_E2E_CHUNKS", "4"))
+            chunks = int(os.environ.get("PGLB_E2E_CHUNKS", "2"))
 
             def e2e_step():
                 # public host-buffer API: upload / aggregate / download pipelined by column chunks

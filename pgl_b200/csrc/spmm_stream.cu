@@ -120,7 +120,7 @@ __device__ __forceinline__ int64_t row_of_slot(const int64_t *__restrict__ indpt
 
 __global__ void __launch_bounds__(256) task_plan_kernel(const int64_t *__restrict__ indptr,
                                                         int64_t n_rows, int64_t E, int64_t T,
-                                                        int64_t ntasks,
+                                                        int64_t snap, int64_t ntasks,
                                                         int64_t *__restrict__ first_row,
                                                         int64_t *__restrict__ start) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,8 +138,9 @@ __global__ void __launch_bounds__(256) task_plan_kernel(const int64_t *__restric
     int64_t r = row_of_slot(indptr, n_rows, a);
     const int64_t s_r = __ldg((const long long *)indptr + r);
     const int64_t e_r = __ldg((const long long *)indptr + r + 1);
-    if (s_r < a && e_r - s_r <= T) {
-        // a short row straddles the nominal boundary: the previous task finishes it
+    if (s_r < a && e_r - s_r <= snap) {
+        // a row of <= snap slots straddles the nominal boundary: the task that holds its first
+        // slot finishes it (tasks whose nominal range lies inside such a row become empty)
         a = e_r;
         r = (a < E) ? row_of_slot(indptr, n_rows, a) : n_rows - 1;
     }
@@ -150,14 +151,28 @@ __global__ void __launch_bounds__(256) task_plan_kernel(const int64_t *__restric
 // ---------------------------------------------------------------------------------------------
 // D <= 128 (one float4 per lane per row)
 // ---------------------------------------------------------------------------------------------
-constexpr int SWY = 5;  // warps per block when an edge operand is staged too (5 * 20 KB)
+// Ring geometry of the D <= 128 kernel.  CFG 0: 32 slots per lane, groups of 8, 7 warps per block
+// (14 per SM).  CFG 1: 16 slots, groups of 4, 14 warps per block (28 per SM): same bytes in flight
+// per SM, twice the warps to hide issue and shared-memory latency.
+template <int CFG, int YM>
+struct Geo {
+    static constexpr int kRing = CFG == 0 ? 32 : 16;
+    static constexpr int kGrp = CFG == 0 ? 8 : 4;
+    static constexpr int kLag = 3;
+    static constexpr int kWarps = CFG == 0 ? (YM ? 5 : 7) : (YM ? 11 : 14);
+    static constexpr int kGpb = 32 / kGrp;       // groups per 32-slot column batch
+    static constexpr int kRg = kRing / kGrp;     // groups per turn of the ring
+    static constexpr int kSmem = kWarps * kRing * (512 + (YM ? 128 : 0));
+};
 
-template <int RK, bool SCALED, int PK, int YM>
-__global__ void __launch_bounds__((YM ? SWY : SW) * 32, 2) spmm_stream128_kernel(const StreamP p) {
+template <int RK, bool SCALED, int PK, int YM, int CFG>
+__global__ void __launch_bounds__(Geo<CFG, YM>::kWarps * 32, 2) spmm_stream128_kernel(const StreamP p) {
+    typedef Geo<CFG, YM> G_;
+    constexpr int RING = G_::kRing, GRP = G_::kGrp, LAG = G_::kLag, GPB = G_::kGpb, RG = G_::kRg;
     // YM 1: message = x[src] (mul|add) y[eid, head(lane)] (send_ue_recv with a per-head or scalar
     // edge operand, the GAT aggregation): the 4-byte operand of every edge rides in a second
     // per-lane ring, fetched with cp.async alongside the feature row.
-    constexpr int W = YM ? SWY : SW;
+    constexpr int W = G_::kWarps;
     // PK 0: int64 column ids; 1: pre-packed uint32 ids (half the index bytes); 2: packed ids whose
     // bit 31 carries the source's L2 policy (hub sources that are gathered again and again are
     // kept with evict_last, the long tail streams through with evict_first so it cannot flush
@@ -258,29 +273,30 @@ __global__ void __launch_bounds__((YM ? SWY : SW) * 32, 2) spmm_stream128_kernel
         const int ngroups = (cnt + GRP - 1) / GRP;
 #pragma unroll 1
         for (int g = 0; g < ngroups + LAG; ++g) {
-            const int sub = g & 3;
+            const int sub = g % GPB;  // position of the group inside its 32-slot column batch
             if (g < ngroups) {
                 if (sub == 0 && g > 0) {
                     const int base = g * GRP;
                     sc_prev = sc_cur;
                     col_cur = col_nxt;
-                    col_nxt = load_col((g >> 2) + 1);
+                    col_nxt = load_col(g / GPB + 1);
                     if (YM) {
                         eid_cur = eid_nxt;
-                        eid_nxt = load_eid((g >> 2) + 1);
+                        eid_nxt = load_eid(g / GPB + 1);
                     }
                     if (SCALED)
                         sc_cur = (base + lane < cnt) ? __ldg(p.scale_src + (col_cur & 0x7fffffffu)) : 1.0f;
                 }
                 const int valid = cnt - g * GRP;
-                const unsigned gaddr = ring + sub * (GRP * 512);
+                const int rs = g % RG;  // ring group slot
+                const unsigned gaddr = ring + rs * (GRP * 512);
 #pragma unroll
                 for (int k = 0; k < GRP; ++k) {
                     const unsigned c = __shfl_sync(0xffffffffu, col_cur, sub * GRP + k);
                     if (YM) {
                         const unsigned eidk = __shfl_sync(0xffffffffu, eid_cur, sub * GRP + k);
                         if (k < valid)
-                            cp_async4(ring2 + (sub * GRP + k) * 128, ylane + (size_t)eidk * p.ldy);
+                            cp_async4(ring2 + (rs * GRP + k) * 128, ylane + (size_t)eidk * p.ldy);
                     }
                     if (k < valid) {
                         if (HOT) {
@@ -296,15 +312,16 @@ __global__ void __launch_bounds__((YM ? SWY : SW) * 32, 2) spmm_stream128_kernel
             if (g >= LAG) {
                 cp_async_wait<LAG>();
                 const int gc = g - LAG;
-                const int csub = gc & 3;
+                const int csub = gc % GPB;
+                const int crs = gc % RG;
                 const int base = gc * GRP;
                 // which register holds the scales of the consumed group's batch
-                const int bcur = (g < ngroups ? g : ngroups - 1) >> 2;
-                const float sc_reg = ((gc >> 2) == bcur) ? sc_cur : sc_prev;
+                const int bcur = (g < ngroups ? g : ngroups - 1) / GPB;
+                const float sc_reg = ((gc / GPB) == bcur) ? sc_cur : sc_prev;
                 int k_end = end_rel - base;  // where the current row ends inside this group
                 int valid = cnt - base;
                 valid = valid > GRP ? GRP : valid;
-                const unsigned gaddr = ring + csub * (GRP * 512);
+                const unsigned gaddr = ring + crs * (GRP * 512);
 #pragma unroll 1
                 for (int k = 0; k < valid; ++k) {
                     while (k == k_end) {
@@ -313,7 +330,7 @@ __global__ void __launch_bounds__((YM ? SWY : SW) * 32, 2) spmm_stream128_kernel
                     }
                     float4 v = lds128(gaddr + k * 512);
                     if (YM) {
-                        const float yv = lds32(ring2 + (csub * GRP + k) * 128);
+                        const float yv = lds32(ring2 + (crs * GRP + k) * 128);
                         if (p.msg_op == PGLB_MSG_MUL) {
                             v.x = __fmul_rn(v.x, yv); v.y = __fmul_rn(v.y, yv);
                             v.z = __fmul_rn(v.z, yv); v.w = __fmul_rn(v.w, yv);
@@ -617,10 +634,10 @@ static StreamWs stream_layout(void *ws, int64_t E, int64_t D, int64_t T) {
     return w;
 }
 
-int64_t stream_task_size() {
-    static int64_t t = 0;
-    if (t == 0) {
-        t = 2048;
+static int64_t env_task_size() {
+    static int64_t t = -1;
+    if (t < 0) {
+        t = 0;
         const char *e = getenv("PGLB_STREAM_TASK");
         if (e) {
             long v = atol(e);
@@ -630,26 +647,59 @@ int64_t stream_task_size() {
     return t;
 }
 
-size_t stream_ws_bytes(int64_t E, int64_t D) { return stream_layout(nullptr, E, D, stream_task_size()).bytes; }
+// Slots per task: 2048 for big graphs, smaller when that would leave fewer than ~4 tasks per
+// resident warp (a 10M-edge graph gets T = 608, a Cora-sized one T = 32).  PGLB_STREAM_TASK pins it
+// (stress tests).
+int64_t stream_task_size(int64_t E) {
+    const int64_t fixed = env_task_size();
+    if (fixed) return fixed;
+    const int64_t target = (int64_t)sm_count() * 28 * 4;
+    int64_t t = (E / target + 31) / 32 * 32;
+    if (t < 32) t = 32;
+    if (t > 2048) t = 2048;
+    return t;
+}
 
-template <int RK, bool SCALED, int PK, int YM>
-static int launch_stream128(const StreamP &p, cudaStream_t stream) {
-    constexpr int W = YM ? SWY : SW;
-    const int smem = W * RING * (512 + (YM ? 128 : 0));
+// Rows of up to this many slots are never cut by a task boundary (=> reduced by one warp in slot
+// order, bit-identical to the sequential loop).
+static int64_t stream_snap(int64_t T) { return env_task_size() ? T : (T > 1024 ? T : 1024); }
+
+size_t stream_ws_bytes(int64_t E, int64_t D) { return stream_layout(nullptr, E, D, stream_task_size(E)).bytes; }
+
+static int stream_cfg() {
+    static int c = -1;
+    if (c < 0) {
+        const char *e = getenv("PGLB_STREAM_CFG");
+        c = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return c;
+}
+
+template <int RK, bool SCALED, int PK, int YM, int CFG>
+static int launch_stream128_cfg(const StreamP &p, cudaStream_t stream) {
+    typedef Geo<CFG, YM> G_;
+    constexpr int W = G_::kWarps;
+    const int smem = G_::kSmem;
     static bool attr_set = false;
     if (!attr_set) {
-        PGLB_CUDA(cudaFuncSetAttribute(spmm_stream128_kernel<RK, SCALED, PK, YM>,
+        PGLB_CUDA(cudaFuncSetAttribute(spmm_stream128_kernel<RK, SCALED, PK, YM, CFG>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     const int64_t blocks = (p.ntasks + W - 1) / W;
     PGLB_CHECK_ARG(blocks <= 0x7fffffffLL, PGLB_ESHAPE, "spmm_stream: grid too large");
-    spmm_stream128_kernel<RK, SCALED, PK, YM><<<(unsigned)blocks, W * 32, smem, stream>>>(p);
+    spmm_stream128_kernel<RK, SCALED, PK, YM, CFG><<<(unsigned)blocks, W * 32, smem, stream>>>(p);
     PGLB_LAUNCH_CHECK("spmm_stream128_kernel");
     const int64_t fblocks = (p.ntasks * 32 + 255) / 256;
     spmm_stream_fixup_kernel<1, RK><<<(unsigned)fblocks, 256, 0, stream>>>(p);
     PGLB_LAUNCH_CHECK("spmm_stream_fixup_kernel");
     return PGLB_OK;
+}
+
+template <int RK, bool SCALED, int PK, int YM>
+static int launch_stream128(const StreamP &p, cudaStream_t stream) {
+    return stream_cfg() == 0 ? launch_stream128_cfg<RK, SCALED, PK, YM, 0>(p, stream)
+                             : launch_stream128_cfg<RK, SCALED, PK, YM, 1>(p, stream);
 }
 
 template <int ITERS, int RK>
@@ -680,7 +730,7 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
                     const uint32_t *cols32, int l2_hints, int accumulate, const int64_t *eid,
                     const float *y, int64_t ldy, int y_bcast, int head_dim, int msg_op, void *ws,
                     size_t ws_bytes, cudaStream_t stream) {
-    const int64_t T = stream_task_size();
+    const int64_t T = stream_task_size(E);
     PGLB_CHECK_ARG(E > 0, PGLB_EINVAL, "spmm_stream_run: needs at least one slot");
     StreamWs w = stream_layout(ws, E, D, T);
     PGLB_CHECK_ARG(ws != nullptr && ws_bytes >= w.bytes, PGLB_EWORKSPACE,
@@ -724,8 +774,8 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
     }
     {
         const int64_t blocks = (w.ntasks + 1 + 255) / 256;
-        task_plan_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indptr, n_dst, E, T, w.ntasks,
-                                                               w.first_row, w.start);
+        task_plan_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indptr, n_dst, E, T, stream_snap(T),
+                                                               w.ntasks, w.first_row, w.start);
         PGLB_LAUNCH_CHECK("task_plan_kernel");
     }
     const int64_t cv = D / 4;

@@ -365,7 +365,7 @@ class Graph(object):
                                   scale_dst=scale_dst)
 
     def send_recv_host(self, feature_host, out_host=None, reduce_func="sum", scale_src=None,
-                       scale_dst=None, chunks=4):
+                       scale_dst=None, chunks=2):
         """``send_recv`` for a feature matrix in pinned HOST memory (result in pinned host memory):
         the graph stays resident, the features stream through the GPU in column chunks with upload,
         aggregation and download overlapped (``ops.HostAggregator``).  Not in the reference (its

@@ -157,7 +157,7 @@ class HostAggregator(object):
     copy-message aggregation are independent) -- so a call costs about one direction of PCIe
     traffic instead of two plus the kernel."""
 
-    def __init__(self, fwd, n_src, n_dst, dim, device, chunks=4):
+    def __init__(self, fwd, n_src, n_dst, dim, device, chunks=2):
         self.fwd, self.n_src, self.n_dst, self.dim = fwd, int(n_src), int(n_dst), int(dim)
         self.device = device
         chunks = max(1, min(int(chunks), self.dim // 4 if self.dim >= 4 else 1))
