@@ -194,6 +194,16 @@ int pglb_maxmin_bwd_f32(const int64_t *src_indptr, const int64_t *dst_of_slot, c
                         const float *out, const float *grad_out, float *grad_x, int64_t n_src,
                         int64_t D, void *stream);
 
+/* GAT attention in one launch (inference path of GATConv, pgl/nn/conv.py:333-335): for every dst row
+ * d and head h, alpha[j,h] = softmax_j( leaky_relu(attn_src[cols[j],h] + attn_dst[d,h]) ) over the
+ * row's slots j -- send_uv(add) + LeakyReLU + edge_softmax without materialising the [E,H] logits.
+ * alpha_slots is in CSR SLOT order (row-contiguous), which is what pglb_spmm_csr_f32 reads
+ * sequentially when eid == NULL.  ws as pglb_edge_softmax_csr_ws. */
+int pglb_gat_attention_csr_f32(const int64_t *indptr, const int64_t *cols, const float *attn_src,
+                               const float *attn_dst, float negative_slope, float *alpha_slots,
+                               int64_t n_rows, int64_t num_edges, int64_t H, void *ws,
+                               size_t ws_bytes, void *stream);
+
 /* norm[i] = clip(float(degree[i]), 1)^-0.5 ; GF.degree_norm (graph_op.py:46-55) */
 int pglb_degree_norm_f32(const int64_t *degree, int64_t n, float *norm, void *stream);
 

@@ -17,32 +17,39 @@ __device__ __forceinline__ float msg_apply(int op, float a, float b) {
 }
 
 // ---- send_uv : out[e,:] = x[src[e],:] op y[dst[e],:] ----------------------------------
+// 2^lsh lanes share one edge (lane l handles vectors l, l + 2^lsh, ...): row / lane come from
+// shifts, not from a 64-bit division per element.
 template <int VEC>
 __global__ void __launch_bounds__(256) send_uv_kernel(const float *__restrict__ x,
                                                       const float *__restrict__ y,
                                                       const int64_t *__restrict__ src, int64_t ss,
                                                       const int64_t *__restrict__ dst, int64_t ds,
-                                                      int64_t E, int D, int op,
+                                                      int64_t E, int D, int lsh, int op,
                                                       float *__restrict__ out) {
     const int dv = D / VEC;
-    const int64_t total = E * dv;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t e = i / dv;
-        const int c = (int)(i - e * dv) * VEC;
+    const int lanes = 1 << lsh;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = (int)(t0 & (lanes - 1));
+    const int64_t estride = ((int64_t)gridDim.x * blockDim.x) >> lsh;
+    for (int64_t e = t0 >> lsh; e < E; e += estride) {
         const int64_t s = __ldg((const long long *)src + e * ss);
         const int64_t d = __ldg((const long long *)dst + e * ds);
-        if (VEC == 4) {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(x + s * D + c));
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(y + d * D + c));
-            float4 r;
-            r.x = msg_apply(op, a.x, b.x);
-            r.y = msg_apply(op, a.y, b.y);
-            r.z = msg_apply(op, a.z, b.z);
-            r.w = msg_apply(op, a.w, b.w);
-            __stcs(reinterpret_cast<float4 *>(out + e * D + c), r);
-        } else {
-            out[e * D + c] = msg_apply(op, __ldg(x + s * D + c), __ldg(y + d * D + c));
+        const float *xr = x + s * D, *yr = y + d * D;
+        float *orow = out + e * D;
+        for (int v = lane; v < dv; v += lanes) {
+            const int c = v * VEC;
+            if (VEC == 4) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(xr + c));
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(yr + c));
+                float4 r;
+                r.x = msg_apply(op, a.x, b.x);
+                r.y = msg_apply(op, a.y, b.y);
+                r.z = msg_apply(op, a.z, b.z);
+                r.w = msg_apply(op, a.w, b.w);
+                __stcs(reinterpret_cast<float4 *>(orow + c), r);
+            } else {
+                orow[c] = msg_apply(op, __ldg(xr + c), __ldg(yr + c));
+            }
         }
     }
 }
@@ -57,36 +64,40 @@ constexpr int MV_UNROLL = 8;
 template <int VEC, bool SCATTER>
 __global__ void __launch_bounds__(256) move_rows_kernel(const float *__restrict__ x, int64_t ldx,
                                                         const int64_t *__restrict__ index,
-                                                        int64_t istride, int64_t n, int D,
+                                                        int64_t istride, int64_t n, int D, int lsh,
                                                         float *__restrict__ out, int64_t ldo) {
+    // 2^lsh lanes share a row (lane l moves vectors l, l + 2^lsh, ...); every thread keeps
+    // MV_UNROLL rows in flight.
     const int dv = D / VEC;
-    const int64_t total = n * dv;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total;
-         i0 += stride * MV_UNROLL) {
-        float4 v4[MV_UNROLL];
-        float v1[MV_UNROLL];
-        int64_t dsto[MV_UNROLL];
+    const int lanes = 1 << lsh;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = (int)(t0 & (lanes - 1));
+    const int64_t rstride = ((int64_t)gridDim.x * blockDim.x) >> lsh;
+    for (int64_t r0 = t0 >> lsh; r0 < n; r0 += rstride * MV_UNROLL) {
+        for (int v = lane; v < dv; v += lanes) {
+            const int c = v * VEC;
+            float4 v4[MV_UNROLL];
+            float v1[MV_UNROLL];
+            int64_t dsto[MV_UNROLL];
 #pragma unroll
-        for (int u = 0; u < MV_UNROLL; ++u) {
-            const int64_t i = i0 + u * stride;
-            dsto[u] = -1;
-            if (i < total) {
-                const int64_t r = i / dv;
-                const int c = (int)(i - r * dv) * VEC;
-                const int64_t k = __ldg((const long long *)index + r * istride);
-                const int64_t rs = SCATTER ? r : k;
-                const int64_t rd = SCATTER ? k : r;
-                dsto[u] = rd * ldo + c;
-                if (VEC == 4) v4[u] = __ldg(reinterpret_cast<const float4 *>(x + rs * ldx + c));
-                else v1[u] = __ldg(x + rs * ldx + c);
+            for (int u = 0; u < MV_UNROLL; ++u) {
+                const int64_t r = r0 + u * rstride;
+                dsto[u] = -1;
+                if (r < n) {
+                    const int64_t k = __ldg((const long long *)index + r * istride);
+                    const int64_t rs = SCATTER ? r : k;
+                    const int64_t rd = SCATTER ? k : r;
+                    dsto[u] = rd * ldo + c;
+                    if (VEC == 4) v4[u] = __ldg(reinterpret_cast<const float4 *>(x + rs * ldx + c));
+                    else v1[u] = __ldg(x + rs * ldx + c);
+                }
             }
-        }
 #pragma unroll
-        for (int u = 0; u < MV_UNROLL; ++u) {
-            if (dsto[u] >= 0) {
-                if (VEC == 4) *reinterpret_cast<float4 *>(out + dsto[u]) = v4[u];
-                else out[dsto[u]] = v1[u];
+            for (int u = 0; u < MV_UNROLL; ++u) {
+                if (dsto[u] >= 0) {
+                    if (VEC == 4) *reinterpret_cast<float4 *>(out + dsto[u]) = v4[u];
+                    else out[dsto[u]] = v1[u];
+                }
             }
         }
     }
@@ -122,65 +133,141 @@ __device__ __forceinline__ float group_reduce(float v, bool is_max, int hp, floa
     return v;
 }
 
-template <int NT>
-__device__ __forceinline__ void softmax_row(const int64_t *__restrict__ eid,
-                                            const float *__restrict__ logits,
-                                            float *__restrict__ out, int64_t b, int64_t e, int H,
-                                            int h0, int hp, float *smem) {
-    const int t = (NT == 32) ? (threadIdx.x & 31) : threadIdx.x;
-    const int head = h0 + (t % hp);
-    const int srow = t / hp;
-    const int sstep = NT / hp;
-    const bool hact = head < H;
+// Where a row's logits come from.  pos(j): element index of slot j (also where the result goes);
+// val(p, head): the logit.
+struct LogitSrc {  // stored logits [E, H], optionally permuted through eid (original edge order)
+    const int64_t *eid;
+    const float *logits;
+    int H;
+    __device__ __forceinline__ int64_t pos(int64_t j) const {
+        return eid ? __ldg((const long long *)eid + j) : j;
+    }
+    __device__ __forceinline__ float val(int64_t p, int64_t /*j*/, int head) const {
+        return __ldg(logits + p * H + head);
+    }
+};
+struct GatSrc {  // GAT attention logits recomputed on the fly, results in CSR slot order
+    const int64_t *cols;
+    const float *attn_src;
+    float ad;  // attn_dst[row, head] of the calling thread
+    float slope;
+    int H;
+    __device__ __forceinline__ int64_t pos(int64_t j) const { return j; }
+    __device__ __forceinline__ float val(int64_t /*p*/, int64_t j, int head) const {
+        const float v = __ldg(attn_src + __ldg((const long long *)cols + j) * H + head) + ad;
+        return v >= 0.0f ? v : v * slope;
+    }
+};
+
+template <int NT, typename Src>
+__device__ __forceinline__ void softmax_row(const Src src, float *__restrict__ out, int64_t b,
+                                            int64_t e, int H, int head, bool hact, int srow,
+                                            int sstep, int hp, float *smem) {
+    // every pass keeps 4 independent load chains in flight per thread: long rows (one CTA per hub
+    // row) are latency bound otherwise
+    constexpr int SU = 4;
     float m = -INFINITY;
-    for (int64_t j = b + srow; j < e; j += sstep) {
-        const int64_t id = eid ? __ldg((const long long *)eid + j) : j;
-        if (hact) m = fmaxf(m, __ldg(logits + id * H + head));
+    for (int64_t j0 = b + srow; j0 < e; j0 += (int64_t)sstep * SU) {
+        float v[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int64_t j = j0 + (int64_t)u * sstep;
+            v[u] = -INFINITY;
+            if (j < e && hact) v[u] = src.val(src.pos(j), j, head);
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u) m = fmaxf(m, v[u]);
     }
     m = group_reduce<NT>(m, true, hp, smem);
     float s = 0.0f;
-    for (int64_t j = b + srow; j < e; j += sstep) {
-        const int64_t id = eid ? __ldg((const long long *)eid + j) : j;
-        if (hact) s += expf(__ldg(logits + id * H + head) - m);
+    for (int64_t j0 = b + srow; j0 < e; j0 += (int64_t)sstep * SU) {
+        float v[SU];
+        bool ok[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int64_t j = j0 + (int64_t)u * sstep;
+            ok[u] = (j < e) && hact;
+            v[u] = 0.0f;
+            if (ok[u]) v[u] = src.val(src.pos(j), j, head);
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u)
+            if (ok[u]) s += expf(v[u] - m);
     }
     s = group_reduce<NT>(s, false, hp, smem);
-    for (int64_t j = b + srow; j < e; j += sstep) {
-        const int64_t id = eid ? __ldg((const long long *)eid + j) : j;
-        if (hact) out[id * H + head] = __fdiv_rn(expf(__ldg(logits + id * H + head) - m), s);
+    for (int64_t j0 = b + srow; j0 < e; j0 += (int64_t)sstep * SU) {
+        float v[SU];
+        int64_t ids[SU];
+#pragma unroll
+        for (int u = 0; u < SU; ++u) {
+            const int64_t j = j0 + (int64_t)u * sstep;
+            ids[u] = -1;
+            if (j < e && hact) {
+                ids[u] = src.pos(j);
+                v[u] = src.val(ids[u], j, head);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SU; ++u)
+            if (ids[u] >= 0) out[ids[u] * H + head] = __fdiv_rn(expf(v[u] - m), s);
     }
 }
 
+// MODE 0: stored logits (edge_softmax / segment_softmax); MODE 1: GAT logits on the fly
+template <int MODE>
 __global__ void __launch_bounds__(256) edge_softmax_warp_kernel(
-    const int64_t *__restrict__ indptr, const int64_t *__restrict__ eid,
-    const float *__restrict__ logits, float *__restrict__ out, int64_t n_rows, int H, int hp,
-    unsigned long long *hub_count, int64_t *hub_rows) {
+    const int64_t *__restrict__ indptr, const int64_t *__restrict__ eid_or_cols,
+    const float *__restrict__ logits_or_asrc, const float *__restrict__ attn_dst, float slope,
+    float *__restrict__ out, int64_t n_rows, int H, int hp, unsigned long long *hub_count,
+    int64_t *hub_rows) {
+    const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int h0 = blockIdx.y * hp;
+    const int head = blockIdx.y * hp + (lane % hp);
+    const bool hact = head < H;
     for (int64_t r = warp; r < n_rows; r += nwarps) {
         const int64_t b = ld_ro(indptr + r), e = ld_ro(indptr + r + 1);
         if (e == b) continue;
         if (e - b > SM_HUB_T) {
-            if ((threadIdx.x & 31) == 0 && blockIdx.y == 0) {
+            if (lane == 0 && blockIdx.y == 0) {
                 unsigned long long s = atomicAdd(hub_count, 1ull);
                 hub_rows[s] = r;
             }
             continue;
         }
-        softmax_row<32>(eid, logits, out, b, e, H, h0, hp, nullptr);
+        if (MODE == 0) {
+            const LogitSrc src{eid_or_cols, logits_or_asrc, H};
+            softmax_row<32>(src, out, b, e, H, head, hact, lane / hp, 32 / hp, hp, nullptr);
+        } else {
+            const GatSrc src{eid_or_cols, logits_or_asrc, hact ? __ldg(attn_dst + r * H + head) : 0.0f,
+                             slope, H};
+            softmax_row<32>(src, out, b, e, H, head, hact, lane / hp, 32 / hp, hp, nullptr);
+        }
     }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(256) edge_softmax_hub_kernel(
-    const int64_t *__restrict__ indptr, const int64_t *__restrict__ eid,
-    const float *__restrict__ logits, float *__restrict__ out, int H, int hp,
-    const unsigned long long *hub_count, const int64_t *hub_rows) {
+    const int64_t *__restrict__ indptr, const int64_t *__restrict__ eid_or_cols,
+    const float *__restrict__ logits_or_asrc, const float *__restrict__ attn_dst, float slope,
+    float *__restrict__ out, int H, int hp, const unsigned long long *hub_count,
+    const int64_t *hub_rows) {
     __shared__ float smem[8 * 32];
     const int64_t n = (int64_t)*hub_count;
-    const int h0 = blockIdx.y * hp;
+    const int t = threadIdx.x;
+    const int head = blockIdx.y * hp + (t % hp);
+    const bool hact = head < H;
     for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
         const int64_t r = hub_rows[i];
-        softmax_row<256>(eid, logits, out, indptr[r], indptr[r + 1], H, h0, hp, smem);
+        const int64_t b = indptr[r], e = indptr[r + 1];
+        if (MODE == 0) {
+            const LogitSrc src{eid_or_cols, logits_or_asrc, H};
+            softmax_row<256>(src, out, b, e, H, head, hact, t / hp, 256 / hp, hp, smem);
+        } else {
+            const GatSrc src{eid_or_cols, logits_or_asrc, hact ? __ldg(attn_dst + r * H + head) : 0.0f,
+                             slope, H};
+            softmax_row<256>(src, out, b, e, H, head, hact, t / hp, 256 / hp, hp, smem);
+        }
         __syncthreads();
     }
 }
@@ -196,6 +283,11 @@ __global__ void __launch_bounds__(256) degree_norm_kernel(const int64_t *__restr
 }
 
 static inline bool a16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline int lane_shift(int64_t dv) {  // lanes per row = min(32, next pow2 >= dv)
+    int l = 0;
+    while ((1 << l) < dv && l < 5) ++l;
+    return l;
+}
 static inline int grid_move(int64_t total) {
     int64_t b = (total + 256 * MV_UNROLL - 1) / (256 * MV_UNROLL);
     const int64_t cap = (int64_t)sm_count() * 2;
@@ -226,11 +318,13 @@ extern "C" int pglb_send_uv_f32(const float *x, const float *y, const int64_t *s
     PGLB_CHECK_ARG(x && y && src && dst && out, PGLB_EINVAL, "pglb_send_uv_f32: NULL pointer");
     PGLB_CHECK_ARG(src_stride >= 1 && dst_stride >= 1, PGLB_EINVAL, "pglb_send_uv_f32: bad stride");
     if (D % 4 == 0 && a16(x) && a16(y) && a16(out)) {
-        send_uv_kernel<4><<<grid_for(E * (D / 4)), 256, 0, stream>>>(
-            x, y, src, src_stride, dst, dst_stride, E, (int)D, msg_op, out);
+        const int l = lane_shift(D / 4);
+        send_uv_kernel<4><<<grid_for(E << l), 256, 0, stream>>>(
+            x, y, src, src_stride, dst, dst_stride, E, (int)D, l, msg_op, out);
     } else {
-        send_uv_kernel<1><<<grid_for(E * D), 256, 0, stream>>>(x, y, src, src_stride, dst,
-                                                                dst_stride, E, (int)D, msg_op, out);
+        const int l = lane_shift(D);
+        send_uv_kernel<1><<<grid_for(E << l), 256, 0, stream>>>(x, y, src, src_stride, dst,
+                                                                 dst_stride, E, (int)D, l, msg_op, out);
     }
     PGLB_LAUNCH_CHECK("send_uv_kernel");
     return PGLB_OK;
@@ -246,11 +340,11 @@ extern "C" int pglb_gather_rows_f32(const float *x, int64_t ldx, const int64_t *
     PGLB_CHECK_ARG(ldx >= D && ldo >= D && index_stride >= 1, PGLB_ESHAPE,
                    "pglb_gather_rows_f32: bad leading dimension / stride");
     if (D % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && a16(x) && a16(out))
-        move_rows_kernel<4, false><<<grid_move(n * (D / 4)), 256, 0, stream>>>(
-            x, ldx, index, index_stride, n, (int)D, out, ldo);
+        move_rows_kernel<4, false><<<grid_move(n << lane_shift(D / 4)), 256, 0, stream>>>(
+            x, ldx, index, index_stride, n, (int)D, lane_shift(D / 4), out, ldo);
     else
-        move_rows_kernel<1, false><<<grid_move(n * D), 256, 0, stream>>>(x, ldx, index, index_stride,
-                                                                        n, (int)D, out, ldo);
+        move_rows_kernel<1, false><<<grid_move(n << lane_shift(D)), 256, 0, stream>>>(
+            x, ldx, index, index_stride, n, (int)D, lane_shift(D), out, ldo);
     PGLB_LAUNCH_CHECK("gather_rows_kernel");
     return PGLB_OK;
 }
@@ -263,11 +357,11 @@ extern "C" int pglb_scatter_rows_f32(const float *x, int64_t ldx, const int64_t 
     PGLB_CHECK_ARG(x && index && out, PGLB_EINVAL, "pglb_scatter_rows_f32: NULL pointer");
     PGLB_CHECK_ARG(ldx >= D && ldo >= D, PGLB_ESHAPE, "pglb_scatter_rows_f32: bad leading dimension");
     if (D % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && a16(x) && a16(out))
-        move_rows_kernel<4, true><<<grid_move(n * (D / 4)), 256, 0, stream>>>(x, ldx, index, 1, n,
-                                                                             (int)D, out, ldo);
+        move_rows_kernel<4, true><<<grid_move(n << lane_shift(D / 4)), 256, 0, stream>>>(
+            x, ldx, index, 1, n, (int)D, lane_shift(D / 4), out, ldo);
     else
-        move_rows_kernel<1, true><<<grid_move(n * D), 256, 0, stream>>>(x, ldx, index, 1, n, (int)D,
-                                                                       out, ldo);
+        move_rows_kernel<1, true><<<grid_move(n << lane_shift(D)), 256, 0, stream>>>(
+            x, ldx, index, 1, n, (int)D, lane_shift(D), out, ldo);
     PGLB_LAUNCH_CHECK("scatter_rows_kernel");
     return PGLB_OK;
 }
@@ -303,14 +397,53 @@ extern "C" int pglb_edge_softmax_csr_f32(const int64_t *indptr, const int64_t *e
     const int64_t cap = (int64_t)sm_count() * 64;
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks, (unsigned)tiles);
-    edge_softmax_warp_kernel<<<grid, 256, 0, stream>>>(indptr, eid, logits, out, n_rows, (int)H, hp,
-                                                       hub_count, hub_rows);
+    edge_softmax_warp_kernel<0><<<grid, 256, 0, stream>>>(indptr, eid, logits, nullptr, 0.0f, out, n_rows,
+                                                          (int)H, hp, hub_count, hub_rows);
     PGLB_LAUNCH_CHECK("edge_softmax_warp_kernel");
     if (E > SM_HUB_T) {
         dim3 hgrid((unsigned)(sm_count() * 4), (unsigned)tiles);
-        edge_softmax_hub_kernel<<<hgrid, 256, 0, stream>>>(indptr, eid, logits, out, (int)H, hp,
-                                                           hub_count, hub_rows);
+        edge_softmax_hub_kernel<0><<<hgrid, 256, 0, stream>>>(indptr, eid, logits, nullptr, 0.0f, out,
+                                                              (int)H, hp, hub_count, hub_rows);
         PGLB_LAUNCH_CHECK("edge_softmax_hub_kernel");
+    }
+    return PGLB_OK;
+}
+
+extern "C" int pglb_gat_attention_csr_f32(const int64_t *indptr, const int64_t *cols,
+                                          const float *attn_src, const float *attn_dst,
+                                          float negative_slope, float *alpha_slots, int64_t n_rows,
+                                          int64_t E, int64_t H, void *ws, size_t ws_bytes,
+                                          void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    PGLB_CHECK_ARG(n_rows >= 0 && E >= 0 && H >= 0 && H <= INT32_MAX, PGLB_EINVAL,
+                   "pglb_gat_attention_csr_f32: bad size");
+    if (n_rows == 0 || E == 0 || H == 0) return PGLB_OK;
+    PGLB_CHECK_ARG(indptr && cols && attn_src && attn_dst && alpha_slots, PGLB_EINVAL,
+                   "pglb_gat_attention_csr_f32: NULL pointer");
+    size_t need = 0;
+    pglb_edge_softmax_csr_ws(E, &need);
+    PGLB_CHECK_ARG(ws && ws_bytes >= need, PGLB_EWORKSPACE,
+                   "pglb_gat_attention_csr_f32: workspace of %zu bytes needed (got %zu)", need, ws_bytes);
+    unsigned long long *hub_count = reinterpret_cast<unsigned long long *>(ws);
+    int64_t *hub_rows = reinterpret_cast<int64_t *>(reinterpret_cast<char *>(ws) + 256);
+    PGLB_CUDA(cudaMemsetAsync(hub_count, 0, 8, stream));
+    int hp = 1;
+    while (hp < H && hp < 32) hp <<= 1;
+    const int tiles = (int)((H + hp - 1) / hp);
+    int64_t blocks = (n_rows + 7) / 8;
+    const int64_t cap = (int64_t)sm_count() * 64;
+    if (blocks > cap) blocks = cap;
+    dim3 grid((unsigned)blocks, (unsigned)tiles);
+    edge_softmax_warp_kernel<1><<<grid, 256, 0, stream>>>(indptr, cols, attn_src, attn_dst, negative_slope,
+                                                          alpha_slots, n_rows, (int)H, hp, hub_count,
+                                                          hub_rows);
+    PGLB_LAUNCH_CHECK("gat_attention_warp_kernel");
+    if (E > SM_HUB_T) {
+        dim3 hgrid((unsigned)(sm_count() * 4), (unsigned)tiles);
+        edge_softmax_hub_kernel<1><<<hgrid, 256, 0, stream>>>(indptr, cols, attn_src, attn_dst,
+                                                              negative_slope, alpha_slots, (int)H, hp,
+                                                              hub_count, hub_rows);
+        PGLB_LAUNCH_CHECK("gat_attention_hub_kernel");
     }
     return PGLB_OK;
 }

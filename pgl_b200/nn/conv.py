@@ -139,6 +139,22 @@ class GATConv(nn.Module):
         feature = feature.reshape(-1, self.num_heads, self.hidden_size)
         attn_src = torch.sum(feature * self.weight_src, dim=-1)
         attn_dst = torch.sum(feature * self.weight_dst, dim=-1)
+        no_attn_drop = self.attn_drop <= 1e-15 or not self.training
+        if not torch.is_grad_enabled() and no_attn_drop and type(graph).__name__ == "Graph":
+            # inference: send_uv + LeakyReLU + edge_softmax in one kernel (logits never stored),
+            # alpha kept in CSR slot order so the aggregation reads it sequentially
+            from .. import ops
+            csr = graph._fwd_csr()
+            alpha = ops.gat_attention_csr(csr, attn_src, attn_dst, self.leaky_relu.negative_slope)
+            output = ops.aggregate_ue_slots(feature, alpha.reshape(-1, self.num_heads, 1), csr,
+                                            int(feature.shape[0]), "mul", "sum")
+            if self.concat:
+                output = output.reshape(-1, self.num_heads * self.hidden_size)
+            else:
+                output = torch.mean(output, dim=1)
+            if self.activation is not None:
+                output = self.activation(output)
+            return output
         alpha = graph.send_uv(attn_src, attn_dst, "add")
         alpha = self.leaky_relu(alpha)
         alpha = GF.edge_softmax(graph, alpha)

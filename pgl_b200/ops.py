@@ -739,6 +739,40 @@ def edge_softmax_csr(indptr, eid, logits, num_edges):
     return out.reshape(shape)
 
 
+def gat_attention_csr(csr, attn_src, attn_dst, negative_slope=0.2):
+    """alpha[slot, h] = softmax over the dst row of leaky_relu(attn_src[src] + attn_dst[dst]) in CSR
+    SLOT order (send_uv + LeakyReLU + edge_softmax fused; inference only)."""
+    require_cuda(attn_src, attn_dst)
+    a_s = _f32_2d(attn_src)
+    a_d = _f32_2d(attn_dst)
+    H = int(a_s.shape[1])
+    E = int(csr["cols"].shape[0])
+    out = torch.empty((E, H), dtype=torch.float32, device=a_s.device)
+    need = ctypes.c_size_t(0)
+    check(lib.pglb_edge_softmax_csr_ws(E, ctypes.byref(need)))
+    ws = workspace(a_s.device, need.value)
+    with torch.cuda.device(a_s.device):
+        check(lib.pglb_gat_attention_csr_f32(_ptr(csr["indptr"]), _ptr(csr["cols"]), _ptr(a_s), _ptr(a_d),
+                                             float(negative_slope), _ptr(out),
+                                             int(csr["indptr"].shape[0]) - 1, E, H, _ptr(ws), ws.numel(),
+                                             _stream()))
+    return out
+
+
+def aggregate_ue_slots(x, y_slots, fwd, n_dst, message_op="mul", reduce_op="sum"):
+    """send_ue_recv whose edge operand is already in CSR slot order (read sequentially)."""
+    require_cuda(x, y_slots)
+    out_feat = tuple(x.shape[1:])
+    cls = classify_bcast(x.shape, y_slots.shape)
+    if cls is None:
+        raise ValueError("pgl_b200: unsupported broadcast for slot-ordered edge operand")
+    mode, hd = cls
+    out = _spmm_raw(fwd["indptr"], fwd["cols"], _f32_2d(x), n_dst, reduce_op, eid=None,
+                    y2=_f32_2d(y_slots), y_bcast=mode, head_dim=hd, msg_op=message_op,
+                    max_degree=fwd.get("max_degree", -1))
+    return out.reshape((n_dst,) + out_feat)
+
+
 def degree_norm(degree):
     require_cuda(degree)
     degree = _i64(degree).contiguous()

@@ -470,6 +470,37 @@ def test_gat_conv_forward(pgl):
         assert rel_err(out, want) <= RTOL
 
 
+def test_gat_fused_inference_matches_unfused(pgl):
+    """The inference fast path (fused attention + slot-ordered aggregation) against the op-by-op
+    path (grad enabled) and the oracle, hubs included."""
+    n, e, H, Dh = 3000, 80000, 8, 16
+    edges = O.chung_lu_edges(n, e, exponent=0.9, seed=231)
+    rng = np.random.default_rng(232)
+    g = make_graph(pgl, edges, n)
+    assert g.adj_dst_index.max_degree > 2048
+    x = rng.standard_normal((n, 64)).astype(np.float32)
+    w, b = _w(rng, 64, H * Dh), _w(rng, H * Dh)
+    wsrc, wdst = _w(rng, H, Dh), _w(rng, H, Dh)
+    conv = pgl.nn.GATConv(64, Dh, feat_drop=0, attn_drop=0, num_heads=H, concat=True).cuda().eval()
+    with torch.no_grad():
+        conv.linear.weight.copy_(dev(w)); conv.linear.bias.copy_(dev(b))
+        conv.weight_src.copy_(dev(wsrc)); conv.weight_dst.copy_(dev(wdst))
+        fused = conv(g, dev(x)).cpu().numpy()
+    unfused = conv(g, dev(x)).detach().cpu().numpy()  # grad enabled -> op-by-op path
+    want = O.gat_conv(edges, n, x, w, b, wsrc, wdst, H, Dh, concat=True)
+    assert rel_err(fused, want) <= RTOL
+    assert rel_err(unfused, want) <= RTOL
+    # the attention kernel alone: slot-ordered alpha == edge_softmax(leaky(send_uv)) permuted
+    f = (x @ w + b).reshape(-1, H, Dh)
+    a_s, a_d = (f * wsrc).sum(-1), (f * wdst).sum(-1)
+    al = O.send_uv(a_s, a_d, edges[:, 0], edges[:, 1], "add")
+    al = np.where(al >= 0, al, al * np.float32(0.2)).astype(np.float32)
+    al = O.edge_softmax(edges, n, al, "dst")
+    eid = g.adj_dst_index._sorted_eid.cpu().numpy()
+    got = pgl.ops.gat_attention_csr(g._fwd_csr(), dev(a_s.astype(np.float32)), dev(a_d.astype(np.float32)), 0.2)
+    assert rel_err(got.cpu().numpy(), al[eid]) <= RTOL
+
+
 def test_backward_sum_mean_vs_torch_reference(pgl):
     """Gradient of the fused aggregation against plain torch fp32 autograd (index_add)."""
     n, e, d = 700, 8000, 24
