@@ -36,8 +36,8 @@ def main():
     conv = pgl.nn.GATConv(128, Dh, feat_drop=0, attn_drop=0, num_heads=H).to(dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
-    def timed(fn, iters=10):
-        for _ in range(3):
+    def timed(fn, iters=20):
+        for _ in range(10):
             fn()
         torch.cuda.synchronize()
         a, b = ev(), ev()
