@@ -204,6 +204,16 @@ int pglb_gat_attention_csr_f32(const int64_t *indptr, const int64_t *cols, const
                                int64_t n_rows, int64_t num_edges, int64_t H, void *ws,
                                size_t ws_bytes, void *stream);
 
+/* The whole GAT aggregation in ONE pass (inference path of GATConv, pgl/nn/conv.py:333-339):
+ *   out[d,h,:] = sum_j softmax_j( leaky_relu(attn_src[cols[j],h] + attn_dst[d,h]) ) * f[cols[j],h,:]
+ * send_uv + LeakyReLU + edge_softmax + send_ue_recv(mul,sum) with an online softmax inside the
+ * wide-row aggregation kernel: neither the logits nor alpha are ever written.  f rows of
+ * H*head_dim <= 128 floats (head_dim % 4 == 0, 16-byte aligned); ws as pglb_spmm_csr_ws(D = H*head_dim). */
+int pglb_gat_fused_csr_f32(const int64_t *indptr, const int64_t *cols, const float *f, int64_t ldf,
+                           const float *attn_src, const float *attn_dst, float negative_slope,
+                           float *out, int64_t ldo, int64_t n_dst, int64_t n_src, int64_t num_edges,
+                           int64_t H, int64_t head_dim, void *ws, size_t ws_bytes, void *stream);
+
 /* norm[i] = clip(float(degree[i]), 1)^-0.5 ; GF.degree_norm (graph_op.py:46-55) */
 int pglb_degree_norm_f32(const int64_t *degree, int64_t n, float *norm, void *stream);
 

@@ -58,6 +58,9 @@ struct StreamP {
     int y_bcast;             // PGLB_BCAST_HEAD or PGLB_BCAST_SCALAR
     int head_dim;
     int msg_op;              // PGLB_MSG_MUL or PGLB_MSG_ADD
+    const float *attn_dst;   // YM 2 (fused GAT): attn_dst[n_rows, H]; y = attn_src[n_src, H]
+    float slope;             // YM 2: LeakyReLU negative slope
+    float *partial_ml;       // YM 2: [2*ntasks, 64] running (max, sum) of cut rows, per lane
     int accumulate;          // SUM only: out = (out_prev + sum) * scale_dst
     int hot_mode;            // 1: hot=evict_last cold=evict_first, 2: hot=last cold=normal, 3: hot=normal cold=first
 };
@@ -189,7 +192,12 @@ __global__ void __launch_bounds__(Geo<CFG, YM>::kWarps * 32, 2) spmm_stream128_k
     const unsigned ring = smem0 + wib * (RING * 512) + lane * 16;
     const unsigned ring2 = smem0 + W * (RING * 512) + wib * (RING * 128) + lane * 4;
     const float *ylane = nullptr;
-    if (YM) ylane = p.y + ((p.y_bcast == PGLB_BCAST_HEAD) ? (lane * 4) / p.head_dim : 0);
+    if (YM) ylane = p.y + ((p.y_bcast == PGLB_BCAST_HEAD && lane * 4 < p.D) ? (lane * 4) / p.head_dim : 0);
+    // YM 2: the whole GAT aggregation in one pass.  y = attn_src (indexed by the SOURCE id, not
+    // the edge id), logit = leaky_relu(attn_src[src,h] + attn_dst[row,h]), and the row is reduced
+    // with an online softmax: running max m, running sum l, accumulator rescaled by exp(m - m').
+    const int yhead = (lane * 4 < p.D) ? (lane * 4) / p.head_dim : 0;
+    float m_run = -INFINITY, l_run = 0.0f, ad = 0.0f;
 
     const bool is_max = (p.reduce_op == PGLB_REDUCE_MAX);
     const float ident = (RK == 0) ? 0.0f : (is_max ? -INFINITY : INFINITY);
@@ -218,11 +226,19 @@ __global__ void __launch_bounds__(Geo<CFG, YM>::kWarps * 32, 2) spmm_stream128_k
             // row `row` is complete: slots [beg_rel, end_rel) relative to a
             if (head) {
                 if (act) *reinterpret_cast<float4 *>(p.partial + (2 * task) * p.dpad + lane * 4) = acc;
+                if (YM == 2) {
+                    p.partial_ml[(2 * task) * 64 + lane * 2] = m_run;
+                    p.partial_ml[(2 * task) * 64 + lane * 2 + 1] = l_run;
+                }
                 head = false;  // the owner task's fix-up finishes this row
             } else if (act) {
                 float4 v = acc;
                 const int deg = end_rel - beg_rel;
                 if (deg == 0) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (YM == 2 && deg != 0) {
+                    v.x = __fdiv_rn(v.x, l_run); v.y = __fdiv_rn(v.y, l_run);
+                    v.z = __fdiv_rn(v.z, l_run); v.w = __fdiv_rn(v.w, l_run);
+                }
                 if (p.accumulate) {
                     const float4 o = *reinterpret_cast<const float4 *>(p.out + row * p.ldo + lane * 4);
                     v.x = __fadd_rn(o.x, v.x); v.y = __fadd_rn(o.y, v.y);
@@ -245,7 +261,13 @@ __global__ void __launch_bounds__(Geo<CFG, YM>::kWarps * 32, 2) spmm_stream128_k
             end_rel = nxt_rel;
             nxt_rel = (row + 2 <= p.n_rows) ? rel(ld_ro(p.indptr + row + 2)) : (1 << 30);
             acc = make_float4(ident, ident, ident, ident);
+            if (YM == 2) {
+                m_run = -INFINITY;
+                l_run = 0.0f;
+                ad = (act && row < p.n_rows) ? __ldg(p.attn_dst + row * p.ldy + yhead) : 0.0f;
+            }
         };
+        if (YM == 2) ad = act ? __ldg(p.attn_dst + row * p.ldy + yhead) : 0.0f;
 
         auto load_col = [&](int batch) -> unsigned {
             const int j = batch * 32 + lane;
@@ -255,7 +277,7 @@ __global__ void __launch_bounds__(Geo<CFG, YM>::kWarps * 32, 2) spmm_stream128_k
         };
         auto load_eid = [&](int batch) -> unsigned {
             const int j = batch * 32 + lane;
-            if (!YM || j >= cnt) return 0u;
+            if (YM != 1 || j >= cnt) return 0u;
             return (unsigned)(p.eid ? ld_stream(p.eid + a + j) : (a + j));
         };
         // 32-bit column ids: the dispatcher routes n_src >= 2^32 to the generic kernel
@@ -280,7 +302,7 @@ __global__ void __launch_bounds__(Geo<CFG, YM>::kWarps * 32, 2) spmm_stream128_k
                     sc_prev = sc_cur;
                     col_cur = col_nxt;
                     col_nxt = load_col(g / GPB + 1);
-                    if (YM) {
+                    if (YM == 1) {
                         eid_cur = eid_nxt;
                         eid_nxt = load_eid(g / GPB + 1);
                     }
@@ -293,11 +315,13 @@ __global__ void __launch_bounds__(Geo<CFG, YM>::kWarps * 32, 2) spmm_stream128_k
 #pragma unroll
                 for (int k = 0; k < GRP; ++k) {
                     const unsigned c = __shfl_sync(0xffffffffu, col_cur, sub * GRP + k);
-                    if (YM) {
+                    if (YM == 1) {
                         const unsigned eidk = __shfl_sync(0xffffffffu, eid_cur, sub * GRP + k);
                         if (k < valid)
                             cp_async4(ring2 + (rs * GRP + k) * 128, ylane + (size_t)eidk * p.ldy);
                     }
+                    if (YM == 2 && k < valid)  // attn_src of the SOURCE node
+                        cp_async4(ring2 + (rs * GRP + k) * 128, ylane + (size_t)c * p.ldy);
                     if (k < valid) {
                         if (HOT) {
                             const uint64_t pol = (c >> 31) ? pol_last : pol_first;
@@ -329,7 +353,19 @@ __global__ void __launch_bounds__(Geo<CFG, YM>::kWarps * 32, 2) spmm_stream128_k
                         k_end = end_rel - base;
                     }
                     float4 v = lds128(gaddr + k * 512);
-                    if (YM) {
+                    if (YM == 2) {
+                        float lg = lds32(ring2 + (crs * GRP + k) * 128) + ad;
+                        lg = lg >= 0.0f ? lg : lg * p.slope;
+                        const float m_new = fmaxf(m_run, lg);
+                        const float sc = expf(m_run - m_new);  // exp(-inf) = 0 for the first slot
+                        const float pe = expf(lg - m_new);
+                        l_run = fmaf(l_run, sc, pe);
+                        acc.x = fmaf(acc.x, sc, pe * v.x); acc.y = fmaf(acc.y, sc, pe * v.y);
+                        acc.z = fmaf(acc.z, sc, pe * v.z); acc.w = fmaf(acc.w, sc, pe * v.w);
+                        m_run = m_new;
+                        continue;
+                    }
+                    if (YM == 1) {
                         const float yv = lds32(ring2 + (crs * GRP + k) * 128);
                         if (p.msg_op == PGLB_MSG_MUL) {
                             v.x = __fmul_rn(v.x, yv); v.y = __fmul_rn(v.y, yv);
@@ -368,6 +404,11 @@ __global__ void __launch_bounds__(Geo<CFG, YM>::kWarps * 32, 2) spmm_stream128_k
             if (act)
                 *reinterpret_cast<float4 *>(p.partial + (head ? (2 * task) : (2 * task + 1)) * p.dpad +
                                             lane * 4) = acc;
+            if (YM == 2) {
+                const int64_t sl = head ? (2 * task) : (2 * task + 1);
+                p.partial_ml[sl * 64 + lane * 2] = m_run;
+                p.partial_ml[sl * 64 + lane * 2 + 1] = l_run;
+            }
             if (!head) tail = row;
         }
     }
@@ -606,11 +647,42 @@ __global__ void __launch_bounds__(256) spmm_stream_fixup_kernel(const StreamP p)
     }
 }
 
+// Fused-GAT fix-up: merge the (acc, m, l) partials of a cut row: M = max m_i,
+// out = sum_i acc_i e^{m_i - M} / sum_i l_i e^{m_i - M}
+__global__ void __launch_bounds__(256) spmm_stream_fixup_gat_kernel(const StreamP p) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= p.ntasks) return;
+    const int64_t r = p.tail_row[t];
+    if (r < 0) return;
+    const int c = lane * 4;
+    if (c >= p.D) return;
+    const int64_t e_r = ld_ro(p.indptr + r + 1);
+    const int64_t u_end = (e_r + p.T - 1) / p.T;
+    float M = p.partial_ml[(2 * t + 1) * 64 + lane * 2];
+    for (int64_t u = t + 1; u < u_end; ++u) M = fmaxf(M, p.partial_ml[(2 * u) * 64 + lane * 2]);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float L = 0.0f;
+    auto add = [&](int64_t slot) {
+        const float w = expf(p.partial_ml[slot * 64 + lane * 2] - M);
+        const float4 v = *reinterpret_cast<const float4 *>(p.partial + slot * p.dpad + c);
+        L = fmaf(p.partial_ml[slot * 64 + lane * 2 + 1], w, L);
+        acc.x = fmaf(v.x, w, acc.x); acc.y = fmaf(v.y, w, acc.y);
+        acc.z = fmaf(v.z, w, acc.z); acc.w = fmaf(v.w, w, acc.w);
+    };
+    add(2 * t + 1);
+    for (int64_t u = t + 1; u < u_end; ++u) add(2 * u);
+    acc.x = __fdiv_rn(acc.x, L); acc.y = __fdiv_rn(acc.y, L);
+    acc.z = __fdiv_rn(acc.z, L); acc.w = __fdiv_rn(acc.w, L);
+    *reinterpret_cast<float4 *>(p.out + r * p.ldo + c) = acc;
+}
+
 struct StreamWs {
     int64_t *first_row;
     int64_t *start;
     int64_t *tail_row;
     float *partial;
+    float *partial_ml;
     int64_t ntasks, dpad;
     size_t bytes;
 };
@@ -630,6 +702,7 @@ static StreamWs stream_layout(void *ws, int64_t E, int64_t D, int64_t T) {
     w.start = reinterpret_cast<int64_t *>(take(sizeof(int64_t) * (w.ntasks + 1)));
     w.tail_row = reinterpret_cast<int64_t *>(take(sizeof(int64_t) * w.ntasks));
     w.partial = reinterpret_cast<float *>(take(sizeof(float) * 2 * w.ntasks * w.dpad));
+    w.partial_ml = reinterpret_cast<float *>(take(sizeof(float) * 2 * w.ntasks * 64));
     w.bytes = off;
     return w;
 }
@@ -691,7 +764,11 @@ static int launch_stream128_cfg(const StreamP &p, cudaStream_t stream) {
     spmm_stream128_kernel<RK, SCALED, PK, YM, CFG><<<(unsigned)blocks, W * 32, smem, stream>>>(p);
     PGLB_LAUNCH_CHECK("spmm_stream128_kernel");
     const int64_t fblocks = (p.ntasks * 32 + 255) / 256;
-    spmm_stream_fixup_kernel<1, RK><<<(unsigned)fblocks, 256, 0, stream>>>(p);
+    if (YM == 2) {
+        spmm_stream_fixup_gat_kernel<<<(unsigned)fblocks, 256, 0, stream>>>(p);
+    } else {
+        spmm_stream_fixup_kernel<1, RK><<<(unsigned)fblocks, 256, 0, stream>>>(p);
+    }
     PGLB_LAUNCH_CHECK("spmm_stream_fixup_kernel");
     return PGLB_OK;
 }
@@ -797,6 +874,51 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
     const int tiles = (int)((cv + 32 * iters - 1) / (32 * iters));
     if (iters == 2) return rk ? launch_stream<2, 1>(p, tiles, stream) : launch_stream<2, 0>(p, tiles, stream);
     return rk ? launch_stream<4, 1>(p, tiles, stream) : launch_stream<4, 0>(p, tiles, stream);
+}
+
+// Single-pass GAT aggregation (inference): out[d,h,:] = sum_j softmax_j(leaky(as[src_j,h] + ad[d,h])) f[src_j,h,:]
+int gat_fused_run(const int64_t *indptr, const int64_t *cols, const float *f, int64_t ldf, float *out,
+                  int64_t ldo, int64_t n_dst, int64_t n_src, int64_t E, int64_t D, int64_t H,
+                  const float *attn_src, const float *attn_dst, float slope, void *ws, size_t ws_bytes,
+                  cudaStream_t stream) {
+    const int64_t T = stream_task_size(E);
+    PGLB_CHECK_ARG(E > 0, PGLB_EINVAL, "gat_fused_run: needs at least one slot");
+    StreamWs w = stream_layout(ws, E, D, T);
+    PGLB_CHECK_ARG(ws != nullptr && ws_bytes >= w.bytes, PGLB_EWORKSPACE,
+                   "pglb_gat_fused_csr_f32: workspace of %zu bytes needed (got %zu)", w.bytes, ws_bytes);
+    StreamP p{};
+    p.indptr = indptr;
+    p.cols = cols;
+    p.x = f;
+    p.ldx = ldf;
+    p.out = out;
+    p.ldo = ldo;
+    p.n_rows = n_dst;
+    p.E = E;
+    p.D = (int)D;
+    p.reduce_op = PGLB_REDUCE_SUM;
+    p.T = T;
+    p.ntasks = w.ntasks;
+    p.first_row = w.first_row;
+    p.start = w.start;
+    p.partial = w.partial;
+    p.partial_ml = w.partial_ml;
+    p.dpad = w.dpad;
+    p.tail_row = w.tail_row;
+    p.y = attn_src;
+    p.ldy = H;
+    p.y_bcast = PGLB_BCAST_HEAD;
+    p.head_dim = (int)(D / H);
+    p.attn_dst = attn_dst;
+    p.slope = slope;
+    p.hot_mode = 1;
+    {
+        const int64_t blocks = (w.ntasks + 1 + 255) / 256;
+        task_plan_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indptr, n_dst, E, T, stream_snap(T),
+                                                               w.ntasks, w.first_row, w.start);
+        PGLB_LAUNCH_CHECK("task_plan_kernel");
+    }
+    return launch_stream128<0, false, 0, 2>(p, stream);
 }
 
 }  // namespace pglb

@@ -145,9 +145,13 @@ class GATConv(nn.Module):
             # alpha kept in CSR slot order so the aggregation reads it sequentially
             from .. import ops
             csr = graph._fwd_csr()
-            alpha = ops.gat_attention_csr(csr, attn_src, attn_dst, self.leaky_relu.negative_slope)
-            output = ops.aggregate_ue_slots(feature, alpha.reshape(-1, self.num_heads, 1), csr,
-                                            int(feature.shape[0]), "mul", "sum")
+            # one pass when the row fits the wide-row kernel (H*Dh in (64, 128]); otherwise the
+            # fused attention kernel + slot-ordered aggregation
+            output = ops.gat_fused(csr, feature, attn_src, attn_dst, self.leaky_relu.negative_slope)
+            if output is None:
+                alpha = ops.gat_attention_csr(csr, attn_src, attn_dst, self.leaky_relu.negative_slope)
+                output = ops.aggregate_ue_slots(feature, alpha.reshape(-1, self.num_heads, 1), csr,
+                                                int(feature.shape[0]), "mul", "sum")
             if self.concat:
                 output = output.reshape(-1, self.num_heads * self.hidden_size)
             else:

@@ -759,6 +759,29 @@ def gat_attention_csr(csr, attn_src, attn_dst, negative_slope=0.2):
     return out
 
 
+def gat_fused(csr, f, attn_src, attn_dst, negative_slope=0.2):
+    """Single-pass GAT aggregation (online softmax in the wide-row kernel).  f [N, H, Dh] with
+    H*Dh <= 128 and Dh % 4 == 0; returns [N, H, Dh], or None when the shape is not supported."""
+    require_cuda(f, attn_src, attn_dst)
+    n, H, Dh = int(f.shape[0]), int(f.shape[1]), int(f.shape[2])
+    if H * Dh > 128 or Dh % 4 or H * Dh <= 64:
+        return None
+    f2 = _f32_2d(f)
+    a_s, a_d = _f32_2d(attn_src), _f32_2d(attn_dst)
+    E = int(csr["cols"].shape[0])
+    n_dst = int(csr["indptr"].shape[0]) - 1
+    out = torch.empty((n_dst, H * Dh), dtype=torch.float32, device=f2.device)
+    need = ctypes.c_size_t(0)
+    check(lib.pglb_spmm_csr_ws(n_dst, E, H * Dh, ctypes.byref(need)))
+    ws = workspace(f2.device, need.value)
+    with torch.cuda.device(f2.device):
+        check(lib.pglb_gat_fused_csr_f32(_ptr(csr["indptr"]), _ptr(csr["cols"]), _ptr(f2), f2.stride(0),
+                                         _ptr(a_s), _ptr(a_d), float(negative_slope), _ptr(out),
+                                         out.stride(0), n_dst, n, E, H, Dh, _ptr(ws), ws.numel(),
+                                         _stream()))
+    return out.reshape(n_dst, H, Dh)
+
+
 def aggregate_ue_slots(x, y_slots, fwd, n_dst, message_op="mul", reduce_op="sum"):
     """send_ue_recv whose edge operand is already in CSR slot order (read sequentially)."""
     require_cuda(x, y_slots)

@@ -60,6 +60,7 @@ def main():
         csr = g._fwd_csr()
         t_att, alpha_s = timed(lambda: pgl.ops.gat_attention_csr(csr, a_s, a_d, 0.2))
         t_ues, _ = timed(lambda: pgl.ops.aggregate_ue_slots(f, alpha_s.reshape(-1, H, 1), csr, n, "mul", "sum"))
+        t_one, _ = timed(lambda: pgl.ops.gat_fused(csr, f, a_s, a_d, 0.2))
         t_gemm, _ = timed(lambda: x @ conv.linear.weight + conv.linear.bias)
     peak = 6582.5
     p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
@@ -71,7 +72,8 @@ def main():
         "workload": "cfg3 RMAT scale 20, 10M edges, GATConv 128 -> 8x16, eval", "max_in_degree": g.adj_dst_index.max_degree,
         "ms": {"send_uv": t_uv, "leaky_relu(torch)": t_lr, "edge_softmax": t_sm, "send_ue_recv": t_ue,
                "attention+aggregation": agg_ms, "linear(fp32 gemm)": t_gemm, "GATConv.forward(fused inference)": t_layer,
-               "fused attention": t_att, "slot-ordered aggregation": t_ues},
+               "fused attention": t_att, "slot-ordered aggregation": t_ues, "single-pass fused GAT aggregation": t_one},
+        "roofline_frac_single_pass": b_alg / (t_one * 1e-3) / 1e9 / peak,
         "roofline_frac_fused_pair": b_alg / ((t_att + t_ues) * 1e-3) / 1e9 / peak,
         "edges_per_s_attention_aggregation": e / (agg_ms * 1e-3),
         "roofline_frac_fused_model": b_alg / (agg_ms * 1e-3) / 1e9 / peak,

@@ -499,6 +499,18 @@ def test_gat_fused_inference_matches_unfused(pgl):
     eid = g.adj_dst_index._sorted_eid.cpu().numpy()
     got = pgl.ops.gat_attention_csr(g._fwd_csr(), dev(a_s.astype(np.float32)), dev(a_d.astype(np.float32)), 0.2)
     assert rel_err(got.cpu().numpy(), al[eid]) <= RTOL
+    # the two inference variants agree: single pass (online softmax) vs attention kernel + aggregation
+    fd = dev(f.astype(np.float32))
+    one = pgl.ops.gat_fused(g._fwd_csr(), fd, dev(a_s.astype(np.float32)), dev(a_d.astype(np.float32)), 0.2)
+    two = pgl.ops.aggregate_ue_slots(fd, got.reshape(-1, H, 1), g._fwd_csr(), n, "mul", "sum")
+    assert one is not None and rel_err(one.cpu().numpy(), two.cpu().numpy()) <= RTOL
+    assert rel_err(one.reshape(n, -1).cpu().numpy(), want) <= RTOL
+    # a narrow layer (H*Dh = 32) is outside the single-pass kernel's shape and takes the two-launch path
+    conv2 = pgl.nn.GATConv(64, 8, feat_drop=0, attn_drop=0, num_heads=4).cuda().eval()
+    with torch.no_grad():
+        y_fused = conv2(g, dev(x))
+    y_ref = conv2(g, dev(x)).detach()
+    assert rel_err(y_fused.cpu().numpy(), y_ref.cpu().numpy()) <= RTOL
 
 
 def test_backward_sum_mean_vs_torch_reference(pgl):
