@@ -356,13 +356,18 @@ __global__ void __launch_bounds__(Geo<CFG, YM>::kWarps * 32, 2) spmm_stream128_k
                     if (YM == 2) {
                         float lg = lds32(ring2 + (crs * GRP + k) * 128) + ad;
                         lg = lg >= 0.0f ? lg : lg * p.slope;
-                        const float m_new = fmaxf(m_run, lg);
-                        const float sc = expf(m_run - m_new);  // exp(-inf) = 0 for the first slot
-                        const float pe = expf(lg - m_new);
-                        l_run = fmaf(l_run, sc, pe);
-                        acc.x = fmaf(acc.x, sc, pe * v.x); acc.y = fmaf(acc.y, sc, pe * v.y);
-                        acc.z = fmaf(acc.z, sc, pe * v.z); acc.w = fmaf(acc.w, sc, pe * v.w);
-                        m_run = m_new;
+                        if (lg <= m_run) {  // common case: the running max stands, one exp
+                            const float pe = expf(lg - m_run);
+                            l_run += pe;
+                            acc.x = fmaf(pe, v.x, acc.x); acc.y = fmaf(pe, v.y, acc.y);
+                            acc.z = fmaf(pe, v.z, acc.z); acc.w = fmaf(pe, v.w, acc.w);
+                        } else {  // new max: rescale what has been accumulated (exp(-inf) = 0 at a row start)
+                            const float sc = expf(m_run - lg);
+                            l_run = fmaf(l_run, sc, 1.0f);
+                            acc.x = fmaf(acc.x, sc, v.x); acc.y = fmaf(acc.y, sc, v.y);
+                            acc.z = fmaf(acc.z, sc, v.z); acc.w = fmaf(acc.w, sc, v.w);
+                            m_run = lg;
+                        }
                         continue;
                     }
                     if (YM == 1) {
