@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) task_plan_kernel(const int64_t *__restric
         return;
     }
     if (t == 0) {
-        first_row[0] = 0;  // task 0 also owns leading empty rows
+        first_row[0] = row_of_slot(indptr, n_rows, 0);  // first non-empty row (E > 0)
         start[0] = 0;
         return;
     }
@@ -260,6 +260,20 @@ __global__ void __launch_bounds__(Geo<CFG, YM>::kWarps * 32, 2) spmm_stream128_k
             beg_rel = end_rel;
             end_rel = nxt_rel;
             nxt_rel = (row + 2 <= p.n_rows) ? rel(ld_ro(p.indptr + row + 2)) : (1 << 30);
+            if (end_rel == beg_rel && row < p.n_rows) {
+                // the next row is empty: jump over the whole run of empty rows (they are zero-filled
+                // by empty_rows_kernel) to the row that owns the next slot -- a single warp must not
+                // walk 10^5 empty rows one by one (RMAT graphs have such runs)
+                const int64_t pos_abs = a + beg_rel;
+                if (pos_abs >= p.E) {
+                    row = p.n_rows;
+                    end_rel = 1 << 30;
+                } else {
+                    row = row_of_slot(p.indptr, p.n_rows, pos_abs);
+                    end_rel = rel(ld_ro(p.indptr + row + 1));
+                    nxt_rel = (row + 2 <= p.n_rows) ? rel(ld_ro(p.indptr + row + 2)) : (1 << 30);
+                }
+            }
             acc = make_float4(ident, ident, ident, ident);
             if (YM == 2) {
                 m_run = -INFINITY;
@@ -501,6 +515,14 @@ __global__ void __launch_bounds__(StreamCfg<ITERS>::kThreads) spmm_stream_kernel
             ++row;
             cur_beg = cur_end;
             if (row < p.n_rows) cur_end = ld_ro(p.indptr + row + 1);
+            if (row < p.n_rows && cur_end == cur_beg) {  // jump over a run of empty rows
+                if (cur_beg >= p.E) {
+                    row = p.n_rows;
+                } else {
+                    row = row_of_slot(p.indptr, p.n_rows, cur_beg);
+                    cur_end = ld_ro(p.indptr + row + 1);
+                }
+            }
 #pragma unroll
             for (int it = 0; it < ITERS; ++it) acc[it] = make_float4(ident, ident, ident, ident);
         };
@@ -682,6 +704,51 @@ __global__ void __launch_bounds__(256) spmm_stream_fixup_gat_kernel(const Stream
     *reinterpret_cast<float4 *>(p.out + r * p.ldo + c) = acc;
 }
 
+// Rows without a slot: zero (or, when accumulating, out_prev * scale_dst).  One warp looks at 32
+// rows at a time; the streaming tasks above never touch empty rows.
+__global__ void __launch_bounds__(256) empty_rows_kernel(const int64_t *__restrict__ indptr,
+                                                         int64_t n_rows, int D, float *__restrict__ out,
+                                                         int64_t ldo, const float *__restrict__ scale_dst,
+                                                         int accumulate) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r0 = warp * 32; r0 < n_rows; r0 += nwarps * 32) {
+        const int64_t r = r0 + lane;
+        bool empty = false;
+        if (r < n_rows) empty = ld_ro(indptr + r + 1) == ld_ro(indptr + r);
+        unsigned mask = __ballot_sync(0xffffffffu, empty);
+        while (mask) {
+            const int i = __ffs(mask) - 1;
+            mask &= mask - 1;
+            float *row = out + (r0 + i) * ldo;
+            for (int c = lane * 4; c < D; c += 128) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (accumulate) {
+                    v = *reinterpret_cast<const float4 *>(row + c);
+                    if (scale_dst) {
+                        const float sd = __ldg(scale_dst + r0 + i);
+                        v.x *= sd; v.y *= sd; v.z *= sd; v.w *= sd;
+                    }
+                }
+                *reinterpret_cast<float4 *>(row + c) = v;
+            }
+        }
+    }
+}
+
+static int launch_empty_rows(const StreamP &p, cudaStream_t stream) {
+    if (p.accumulate && !p.scale_dst) return PGLB_OK;  // out_prev + 0 unchanged
+    int64_t blocks = (p.n_rows + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    empty_rows_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p.indptr, p.n_rows, p.D, p.out, p.ldo,
+                                                           p.scale_dst, p.accumulate);
+    PGLB_LAUNCH_CHECK("empty_rows_kernel");
+    return PGLB_OK;
+}
+
 struct StreamWs {
     int64_t *first_row;
     int64_t *start;
@@ -860,6 +927,10 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
                                                                w.ntasks, w.first_row, w.start);
         PGLB_LAUNCH_CHECK("task_plan_kernel");
     }
+    {
+        const int rc = launch_empty_rows(p, stream);
+        if (rc) return rc;
+    }
     const int64_t cv = D / 4;
     const int rk = (reduce_op >= PGLB_REDUCE_MAX) ? 1 : 0;
     const bool small_ids = (cols ? n_src : E) < 0x7fffffffLL && ldx * 4 < 0xffffffffLL;
@@ -922,6 +993,10 @@ int gat_fused_run(const int64_t *indptr, const int64_t *cols, const float *f, in
         task_plan_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indptr, n_dst, E, T, stream_snap(T),
                                                                w.ntasks, w.first_row, w.start);
         PGLB_LAUNCH_CHECK("task_plan_kernel");
+    }
+    {
+        const int rc = launch_empty_rows(p, stream);
+        if (rc) return rc;
     }
     return launch_stream128<0, false, 0, 2>(p, stream);
 }
