@@ -430,7 +430,7 @@ def main_ours(args):
                    "packed_cols": packed is not None, "l2_hints": bool(packed and packed[1])},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
                      "frac": achieved / hbm_gbs, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes": b_alg, "kernel": "spmm_stream128_kernel<0,1> (+ task_plan + fix-up kernels)",
+                     "algorithmic_bytes": b_alg, "kernel": "spmm_stream128_kernel<RK=0,SCALED=1,PK=2,YM=0,CFG=1> (+ task_plan, empty_rows, fix-up kernels)",
                      "kernel_ms_mean": kern_ms, "kernel_ms_p10": per[len(per) // 10],
                      "kernel_ms_p90": per[(len(per) * 9) // 10]},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
