@@ -5,7 +5,7 @@ import os
 from ctypes import POINTER, c_char_p, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpglb.so")
+LIB_PATH = os.environ.get("PGLB_LIB") or os.path.join(_HERE, "libpglb.so")
 METIS_PATH = os.path.join(_HERE, "third_party", "libmetis_i64.so")
 
 PGLB_OK = 0

@@ -121,6 +121,12 @@ __device__ __forceinline__ int64_t row_of_slot(const int64_t *__restrict__ indpt
     return lo - 1;
 }
 
+// out-of-line copy for the (rare) empty-row jump inside the streaming kernels: keeps the binary
+// search out of their register allocation and instruction stream
+__device__ __noinline__ int64_t row_of_slot_cold(const int64_t *indptr, int64_t n_rows, int64_t v) {
+    return row_of_slot(indptr, n_rows, v);
+}
+
 __global__ void __launch_bounds__(256) task_plan_kernel(const int64_t *__restrict__ indptr,
                                                         int64_t n_rows, int64_t E, int64_t T,
                                                         int64_t snap, int64_t ntasks,
@@ -269,7 +275,7 @@ __global__ void __launch_bounds__(Geo<CFG, YM>::kWarps * 32, 2) spmm_stream128_k
                     row = p.n_rows;
                     end_rel = 1 << 30;
                 } else {
-                    row = row_of_slot(p.indptr, p.n_rows, pos_abs);
+                    row = row_of_slot_cold(p.indptr, p.n_rows, pos_abs);
                     end_rel = rel(ld_ro(p.indptr + row + 1));
                     nxt_rel = (row + 2 <= p.n_rows) ? rel(ld_ro(p.indptr + row + 2)) : (1 << 30);
                 }
@@ -519,7 +525,7 @@ __global__ void __launch_bounds__(StreamCfg<ITERS>::kThreads) spmm_stream_kernel
                 if (cur_beg >= p.E) {
                     row = p.n_rows;
                 } else {
-                    row = row_of_slot(p.indptr, p.n_rows, cur_beg);
+                    row = row_of_slot_cold(p.indptr, p.n_rows, cur_beg);
                     cur_end = ld_ro(p.indptr + row + 1);
                 }
             }

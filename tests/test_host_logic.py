@@ -1,0 +1,67 @@
+"""CPU tests of host-side helpers that need no device: broadcast classification, partition
+helpers, the builder, workspace sizing through the C-ABI."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+
+def test_classify_bcast():
+    from pgl_b200 import ops
+    from pgl_b200._lib import BCAST_FULL, BCAST_HEAD, BCAST_SCALAR
+    assert ops.classify_bcast((10, 8, 16), (50, 8, 1)) == (BCAST_HEAD, 16)
+    assert ops.classify_bcast((10, 8, 16), (50, 1, 1)) == (BCAST_SCALAR, 1)
+    assert ops.classify_bcast((10, 8, 16), (50, 8, 16)) == (BCAST_FULL, 1)
+    assert ops.classify_bcast((10, 128), (50, 1)) == (BCAST_SCALAR, 1)
+    assert ops.classify_bcast((10, 2, 3, 4), (50, 2, 1, 1)) == (BCAST_HEAD, 12)
+    assert ops.classify_bcast((10, 8, 16), (50, 1, 16)) is None  # needs expand()
+
+
+def test_workspace_queries_and_version():
+    from pgl_b200 import _lib
+    lib = _lib.lib
+    need = ctypes.c_size_t(0)
+    _lib.check(lib.pglb_spmm_csr_ws(10_000_000, 100_000_000, 128, ctypes.byref(need)))
+    assert 0 < need.value < (1 << 30)  # partial buffers of the cfg5 aggregation stay well below 1 GB
+    small = ctypes.c_size_t(0)
+    _lib.check(lib.pglb_spmm_csr_ws(100, 1000, 128, ctypes.byref(small)))
+    assert small.value <= need.value
+    _lib.check(lib.pglb_edge_softmax_csr_ws(1000, ctypes.byref(small)))
+    assert small.value >= 256
+    assert isinstance(_lib.launch_count(), int)
+    # host-only entry points validate before touching CUDA
+    assert lib.pglb_memcpy2d_async(None, 0, None, 0, 0, 0, 1, None) == 0
+    assert lib.pglb_memcpy2d_async(None, 16, None, 16, 16, 1, 1, None) == -1
+    assert lib.pglb_ipc_open(None, None) == -1
+    assert lib.pglb_gat_fused_csr_f32(None, None, None, 128, None, None, 0.2, None, 128, 10, 10, 5, 8,
+                                      20, None, 0, None) == -4  # H*head_dim > 128: unsupported shape
+
+
+def test_block_partition_and_relabel():
+    import pgl_b200 as pgl
+    from pgl_b200.distributed.halo import block_offsets, relabel_by_partition
+    p = pgl.partition.block_partition(10, 4)
+    assert p.tolist() == [0, 0, 0, 1, 1, 1, 2, 2, 2, 3]
+    new_id, off = relabel_by_partition(p, 4)
+    assert off == block_offsets(10, 4) and new_id.tolist() == list(range(10))
+
+
+def test_builder_is_loadable_without_the_library():
+    import __graft_entry__ as ge
+    b = ge.load_builder()
+    assert os.path.basename(b.LIB) == "libpglb.so" and callable(b.build_all)
+    # up to date => no-op
+    assert b.build_lib() == b.LIB
+
+
+def test_gen_edges_and_bytes_model():
+    import torch
+    import bench
+    e = bench.gen_edges(torch, 1000, 5000, 0.8, 7, "cpu")
+    assert e.shape == (5000, 2) and int(e.min()) >= 0 and int(e.max()) < 1000
+    # 572 B/edge at D=128, N/E = 0.1 (+ the two norm vectors)
+    b = bench.algorithmic_bytes(10_000_000, 100_000_000, 128)
+    assert abs(b / 100_000_000 - 572.8) < 0.1
+    n_s, src, dst = bench.cpu_sample_problem(e.numpy(), 1000, 0.1)
+    assert n_s == 100 and (dst < 100).all() and len(src) == len(dst)
