@@ -65,3 +65,22 @@ def test_gen_edges_and_bytes_model():
     assert abs(b / 100_000_000 - 572.8) < 0.1
     n_s, src, dst = bench.cpu_sample_problem(e.numpy(), 1000, 0.1)
     assert n_s == 100 and (dst < 100).all() and len(src) == len(dst)
+
+
+def test_relabel_matches_reference_graph_kernel():
+    from pgl_b200.utils import relabel
+    from oracle import build as obuild
+    rng = np.random.default_rng(3)
+    old = rng.permutation(50)[:20].astype(np.int64)
+    reindex = {int(o): i for i, o in enumerate(old)}
+    nodes = rng.choice(old, 30)
+    edges = rng.choice(old, (40, 2)).astype(np.int64)
+    eid = rng.integers(0, 40, 15).astype(np.int64)
+    mn = relabel.map_nodes(nodes, reindex)
+    me = relabel.map_edges(eid, edges, reindex)
+    assert mn.tolist() == [reindex[int(v)] for v in nodes]
+    assert me.tolist() == [[reindex[int(a)], reindex[int(b)]] for a, b in edges[eid]]
+    gk = obuild.load_ref_graph_kernel()
+    if gk is not None:  # the reference's own Cython helpers (build container only)
+        assert (np.asarray(gk.map_nodes(nodes, reindex)) == mn).all()
+        assert (np.asarray(gk.map_edges(eid, edges, reindex)) == me).all()
