@@ -4,7 +4,8 @@
 
 namespace pglb {
 
-constexpr int64_t SM_HUB_T = 2048;  // rows longer than this use one CTA instead of one warp
+constexpr int64_t SM_HUB_T = 256;  // rows longer than this use one CTA (8 warps) instead of one warp:
+                                   // a 2000-slot row costs a single warp ~0.5 ms of dependent loads
 
 __device__ __forceinline__ float msg_apply(int op, float a, float b) {
     switch (op) {
@@ -163,9 +164,9 @@ template <int NT, typename Src>
 __device__ __forceinline__ void softmax_row(const Src src, float *__restrict__ out, int64_t b,
                                             int64_t e, int H, int head, bool hact, int srow,
                                             int sstep, int hp, float *smem) {
-    // every pass keeps 4 independent load chains in flight per thread: long rows (one CTA per hub
+    // every pass keeps 8 independent load chains in flight per thread: long rows (one CTA per hub
     // row) are latency bound otherwise
-    constexpr int SU = 4;
+    constexpr int SU = 8;
     float m = -INFINITY;
     for (int64_t j0 = b + srow; j0 < e; j0 += (int64_t)sstep * SU) {
         float v[SU];
@@ -401,7 +402,7 @@ extern "C" int pglb_edge_softmax_csr_f32(const int64_t *indptr, const int64_t *e
                                                           (int)H, hp, hub_count, hub_rows);
     PGLB_LAUNCH_CHECK("edge_softmax_warp_kernel");
     if (E > SM_HUB_T) {
-        dim3 hgrid((unsigned)(sm_count() * 4), (unsigned)tiles);
+        dim3 hgrid((unsigned)(sm_count() * 8), (unsigned)tiles);
         edge_softmax_hub_kernel<0><<<hgrid, 256, 0, stream>>>(indptr, eid, logits, nullptr, 0.0f, out,
                                                               (int)H, hp, hub_count, hub_rows);
         PGLB_LAUNCH_CHECK("edge_softmax_hub_kernel");
@@ -439,7 +440,7 @@ extern "C" int pglb_gat_attention_csr_f32(const int64_t *indptr, const int64_t *
                                                           hub_rows);
     PGLB_LAUNCH_CHECK("gat_attention_warp_kernel");
     if (E > SM_HUB_T) {
-        dim3 hgrid((unsigned)(sm_count() * 4), (unsigned)tiles);
+        dim3 hgrid((unsigned)(sm_count() * 8), (unsigned)tiles);
         edge_softmax_hub_kernel<1><<<hgrid, 256, 0, stream>>>(indptr, cols, attn_src, attn_dst,
                                                               negative_slope, alpha_slots, (int)H, hp,
                                                               hub_count, hub_rows);
