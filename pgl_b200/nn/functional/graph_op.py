@@ -1,6 +1,5 @@
 """Graph functional ops on the send/recv path (mirror of reference
 pgl/nn/functional/graph_op.py:29-55,101-123)."""
-import torch
 
 from ... import math, ops
 

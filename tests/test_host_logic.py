@@ -84,3 +84,26 @@ def test_relabel_matches_reference_graph_kernel():
     if gk is not None:  # the reference's own Cython helpers (build container only)
         assert (np.asarray(gk.map_nodes(nodes, reindex)) == mn).all()
         assert (np.asarray(gk.map_edges(eid, edges, reindex)) == me).all()
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference runs anywhere (no GPU, oracle port only) and prints one JSON line
+    with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--nodes",
+                        "20000", "--edges", "200000", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=300, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+              "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["cores"] >= 1
+    # non-zero ranks of a torchrun launch exit 0 without work
+    r2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference"],
+                        capture_output=True, text=True, timeout=120, env=dict(os.environ, RANK="1", CUDA_VISIBLE_DEVICES=""))
+    assert r2.returncode == 0 and r2.stdout.strip() == ""
