@@ -2,15 +2,135 @@
 // counting sort (pgl/graph_kernel.pyx:59-88): degree histogram, exclusive scan, and a
 // STABLE key sort of (u, edge id) so that every bucket keeps ascending edge id.
 //
-// The key sort and the scans use CUB (device-wide LSD radix sort is stable by construction;
-// CUB ships inside the CUDA toolkit and is compiled into this library for sm_100a).  It is
-// one-off index preparation, cached on the EdgeIndex; the per-layer hot loop never calls it.
-#include <cub/cub.cuh>
+// Everything here is hand-written (no CUB / Thrust): a three-kernel multi-block int64 scan and an
+// LSD radix sort of (key, value) pairs, 8 bits per pass.  A pass is (1) per-block digit histograms,
+// (2) one scan of the digit-major [256 x blocks] table, (3) a scatter in which every warp ranks its
+// contiguous sub-tile in order (__match_any_sync + popc, so equal digits keep their order), the
+// block stages the tile in shared memory grouped by digit and writes each digit run coalesced.
+// Order inside a digit is preserved at every level (lane, warp, block, grid) => the sort is stable
+// => sorted_eid is ascending inside every row, exactly like the reference's counting sort.
+// One-off index preparation, cached on the EdgeIndex; the per-layer hot loop never calls it.
+#include <algorithm>
 
 #include "common.cuh"
 
 namespace pglb {
 
+// ---- multi-block scan of int64 ---------------------------------------------------------------
+constexpr int SCAN_T = 256;
+constexpr int SCAN_IPT = 8;
+constexpr int SCAN_TILE = SCAN_T * SCAN_IPT;
+
+__device__ __forceinline__ int64_t block_exclusive_scan_256(int64_t v, int64_t *total) {
+    // exclusive prefix of v over the 256 threads of the block
+    __shared__ int64_t wsum[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();  // protects wsum against the previous use
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    int64_t base = 0, tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (j < w) base += wsum[j];
+        tot += wsum[j];
+    }
+    if (total) *total = tot;
+    return base + incl - v;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_tile_sums_kernel(const int64_t *__restrict__ in, int64_t n,
+                                                                int64_t *__restrict__ sums) {
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    int64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; ++k) {
+        const int64_t i = base + k * SCAN_T + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+    int64_t tot;
+    block_exclusive_scan_256(s, &tot);
+    if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+
+// one block: sums[] -> exclusive prefix in place
+__global__ void __launch_bounds__(SCAN_T) scan_sums_kernel(int64_t *sums, int64_t nb) {
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t b0 = 0; b0 < nb; b0 += SCAN_T) {
+        const int64_t i = b0 + threadIdx.x;
+        const int64_t v = i < nb ? sums[i] : 0;
+        int64_t tot;
+        const int64_t ex = block_exclusive_scan_256(v, &tot);
+        const int64_t c = carry;
+        if (i < nb) sums[i] = c + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry = c + tot;
+        __syncthreads();
+    }
+}
+
+// out[i] = (inclusive ? in[i] : 0) + sum_{j<i} in[j]; thread t owns SCAN_IPT consecutive items
+__global__ void __launch_bounds__(SCAN_T) scan_apply_kernel(const int64_t *__restrict__ in,
+                                                            int64_t *__restrict__ out, int64_t n,
+                                                            const int64_t *__restrict__ sums,
+                                                            int inclusive) {
+    __shared__ int64_t tile[SCAN_TILE];
+    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; ++k) {
+        const int64_t i = base + k * SCAN_T + threadIdx.x;
+        tile[k * SCAN_T + threadIdx.x] = i < n ? in[i] : 0;
+    }
+    __syncthreads();
+    int64_t loc[SCAN_IPT];
+    int64_t s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; ++k) {
+        loc[k] = tile[threadIdx.x * SCAN_IPT + k];
+        s += loc[k];
+    }
+    int64_t run = sums[blockIdx.x] + block_exclusive_scan_256(s, nullptr);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; ++k) {
+        const int64_t ex = run;
+        run += loc[k];
+        tile[threadIdx.x * SCAN_IPT + k] = inclusive ? run : ex;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SCAN_IPT; ++k) {
+        const int64_t i = base + k * SCAN_T + threadIdx.x;
+        if (i < n) out[i] = tile[k * SCAN_T + threadIdx.x];
+    }
+}
+
+static inline int64_t scan_blocks(int64_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+static inline size_t scan_ws_bytes(int64_t n) { return align_up(sizeof(int64_t) * (size_t)std::max<int64_t>(scan_blocks(n), 1), 256); }
+
+// in and out may alias.  tmp: scan_ws_bytes(n).
+static int scan_i64(const int64_t *in, int64_t *out, int64_t n, int inclusive, void *tmp,
+                    cudaStream_t stream) {
+    if (n <= 0) return PGLB_OK;
+    const int64_t nb = scan_blocks(n);
+    int64_t *sums = reinterpret_cast<int64_t *>(tmp);
+    scan_tile_sums_kernel<<<(unsigned)nb, SCAN_T, 0, stream>>>(in, n, sums);
+    PGLB_LAUNCH_CHECK("scan_tile_sums_kernel");
+    scan_sums_kernel<<<1, SCAN_T, 0, stream>>>(sums, nb);
+    PGLB_LAUNCH_CHECK("scan_sums_kernel");
+    scan_apply_kernel<<<(unsigned)nb, SCAN_T, 0, stream>>>(in, out, n, sums, inclusive);
+    PGLB_LAUNCH_CHECK("scan_apply_kernel");
+    return PGLB_OK;
+}
+
+// ---- key packing / result emission -----------------------------------------------------------
 template <typename KeyT, typename ValT>
 __global__ void __launch_bounds__(256) pack_keys_kernel(const int64_t *u, int64_t u_stride,
                                                         int64_t E, KeyT *keys, ValT *vals,
@@ -47,74 +167,194 @@ static int key_bits(int64_t n) {
     return b;
 }
 
-template <typename KeyT, typename ValT>
+// ---- stable LSD radix sort of pairs, 8 bits per pass -------------------------------------------
+template <typename KeyT>
+__device__ __forceinline__ unsigned digit_of(KeyT k, int shift) {
+    return (unsigned)((k >> shift) & 0xff);
+}
+
+// table[d * nb + b] = number of keys of block b's tile whose current digit is d
+template <typename KeyT, int IPW>
+__global__ void __launch_bounds__(256) rs_hist_kernel(const KeyT *__restrict__ keys, int64_t n, int shift,
+                                                      int64_t nb, int64_t *__restrict__ table) {
+    constexpr int TILE = 8 * IPW;
+    __shared__ unsigned hist[256];
+    hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * TILE;
+    for (int i = threadIdx.x; i < TILE; i += 256) {
+        const int64_t g = base + i;
+        if (g < n) atomicAdd(&hist[digit_of(keys[g], shift)], 1u);
+    }
+    __syncthreads();
+    table[(int64_t)threadIdx.x * nb + blockIdx.x] = hist[threadIdx.x];
+}
+
+// table has been exclusive-scanned in digit-major order: table[d*nb+b] = first output slot of the
+// run of digit d contributed by block b
+template <typename KeyT, typename ValT, int IPW>
+__global__ void __launch_bounds__(256) rs_scatter_kernel(const KeyT *__restrict__ kin,
+                                                         const ValT *__restrict__ vin,
+                                                         KeyT *__restrict__ kout, ValT *__restrict__ vout,
+                                                         int64_t n, int shift, int64_t nb,
+                                                         const int64_t *__restrict__ table) {
+    constexpr int TILE = 8 * IPW;
+    __shared__ unsigned whist[8][256];  // per-warp digit counts, then running local bases
+    __shared__ unsigned bpre[256];      // local position where the block's run of digit d starts
+    __shared__ unsigned wsum[8];
+    __shared__ int64_t goff[256];
+    __shared__ KeyT skey[TILE];
+    __shared__ ValT sval[TILE];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t base = (int64_t)blockIdx.x * TILE;
+    const int64_t rem = n - base;
+    const int cnt = rem < TILE ? (int)rem : TILE;
+
+    for (int i = tid; i < 8 * 256; i += 256) (&whist[0][0])[i] = 0;
+    __syncthreads();
+    // (a) warp w owns the contiguous items [w*IPW, (w+1)*IPW)
+    for (int c = 0; c < IPW; c += 32) {
+        const int i = w * IPW + c + lane;
+        if (i < cnt) atomicAdd(&whist[w][digit_of(kin[base + i], shift)], 1u);
+    }
+    __syncthreads();
+    // (b) thread d: exclusive prefix over the warps for digit d, then over the digits for the block
+    {
+        const int d = tid;
+        unsigned tot = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const unsigned c = whist[j][d];
+            whist[j][d] = tot;
+            tot += c;
+        }
+        unsigned incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[w] = incl;
+        __syncthreads();
+        unsigned wb = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < w) wb += wsum[j];
+        bpre[d] = wb + incl - tot;
+        goff[d] = table[(int64_t)d * nb + blockIdx.x];
+    }
+    __syncthreads();
+    // (c) every warp walks its sub-tile in order; equal digits inside a 32-item chunk are ranked by
+    //     lane, chunks are sequential => stable.  Items land in shared memory grouped by digit.
+    for (int c = 0; c < IPW; c += 32) {
+        const int i = w * IPW + c + lane;
+        const bool valid = i < cnt;
+        KeyT k = 0;
+        ValT v = 0;
+        unsigned d = 0;
+        if (valid) {
+            k = kin[base + i];
+            v = vin[base + i];
+            d = digit_of(k, shift);
+        }
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const unsigned m = __match_any_sync(act, d);
+            const unsigned r = __popc(m & ((1u << lane) - 1u));
+            const unsigned lp = bpre[d] + whist[w][d] + r;
+            skey[lp] = k;
+            sval[lp] = v;
+            __syncwarp(act);  // every lane has read whist[w][d] before its leader bumps it
+            if (r == 0) whist[w][d] += __popc(m);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    // (d) write out: consecutive local positions of one digit are consecutive global slots
+    for (int lp = tid; lp < cnt; lp += 256) {
+        const KeyT k = skey[lp];
+        const unsigned d = digit_of(k, shift);
+        const int64_t g = goff[d] + (int64_t)(lp - bpre[d]);
+        kout[g] = k;
+        vout[g] = sval[lp];
+    }
+}
+
+template <typename KeyT>
+struct SortGeo {
+    static constexpr int kIpw = sizeof(KeyT) == 4 ? 512 : 256;  // tile = 4096 (32-bit) / 2048 (64-bit) pairs
+    static constexpr int kTile = 8 * kIpw;
+};
+
 struct SortPlan {
-    size_t keys_in, keys_out, vals_in, vals_out, scan_tmp, sort_tmp, total;
-    size_t scan_tmp_bytes, sort_tmp_bytes;
+    size_t keys_a, keys_b, vals_a, vals_b, table, scan_tmp, total;
+    int64_t nb;
 };
 
 template <typename KeyT, typename ValT>
-static cudaError_t plan(int64_t E, int64_t N, SortPlan<KeyT, ValT> &pl) {
+static SortPlan plan(int64_t E, int64_t N) {
+    SortPlan pl;
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t r = off;
         off += align_up(bytes ? bytes : 1, 256);
         return r;
     };
-    pl.keys_in = take(sizeof(KeyT) * E);
-    pl.keys_out = take(sizeof(KeyT) * E);
-    pl.vals_in = take(sizeof(ValT) * E);
-    pl.vals_out = take(sizeof(ValT) * E);
-    pl.scan_tmp_bytes = 0;
-    cudaError_t e = cub::DeviceScan::InclusiveSum(nullptr, pl.scan_tmp_bytes, (const int64_t *)nullptr,
-                                                  (int64_t *)nullptr, N);
-    if (e != cudaSuccess) return e;
-    pl.sort_tmp_bytes = 0;
-    e = cub::DeviceRadixSort::SortPairs(nullptr, pl.sort_tmp_bytes, (const KeyT *)nullptr,
-                                        (KeyT *)nullptr, (const ValT *)nullptr, (ValT *)nullptr,
-                                        E, 0, key_bits(N));
-    if (e != cudaSuccess) return e;
-    pl.scan_tmp = take(pl.scan_tmp_bytes);
-    pl.sort_tmp = take(pl.sort_tmp_bytes);
+    pl.nb = (E + SortGeo<KeyT>::kTile - 1) / SortGeo<KeyT>::kTile;
+    pl.keys_a = take(sizeof(KeyT) * E);
+    pl.keys_b = take(sizeof(KeyT) * E);
+    pl.vals_a = take(sizeof(ValT) * E);
+    pl.vals_b = take(sizeof(ValT) * E);
+    pl.table = take(sizeof(int64_t) * 256 * (size_t)std::max<int64_t>(pl.nb, 1));
+    const int64_t longest = std::max<int64_t>(256 * std::max<int64_t>(pl.nb, 1), N);
+    pl.scan_tmp = take(scan_ws_bytes(longest));
     pl.total = off;
-    return cudaSuccess;
+    return pl;
 }
 
 template <typename KeyT, typename ValT>
 static int run(const int64_t *u, int64_t us, const int64_t *v, int64_t vs, int64_t E, int64_t N,
                int64_t *degree, int64_t *indptr, int64_t *su, int64_t *sv, int64_t *se, void *ws,
                size_t ws_bytes, cudaStream_t stream) {
-    SortPlan<KeyT, ValT> pl;
-    PGLB_CUDA((plan<KeyT, ValT>(E, N, pl)));
+    const SortPlan pl = plan<KeyT, ValT>(E, N);
     PGLB_CHECK_ARG(ws_bytes >= pl.total, PGLB_EWORKSPACE,
                    "pglb_csr_build: workspace of %zu bytes needed (got %zu)", pl.total, ws_bytes);
     char *base = reinterpret_cast<char *>(ws);
-    KeyT *keys_in = reinterpret_cast<KeyT *>(base + pl.keys_in);
-    KeyT *keys_out = reinterpret_cast<KeyT *>(base + pl.keys_out);
-    ValT *vals_in = reinterpret_cast<ValT *>(base + pl.vals_in);
-    ValT *vals_out = reinterpret_cast<ValT *>(base + pl.vals_out);
+    KeyT *ka = reinterpret_cast<KeyT *>(base + pl.keys_a);
+    KeyT *kb = reinterpret_cast<KeyT *>(base + pl.keys_b);
+    ValT *va = reinterpret_cast<ValT *>(base + pl.vals_a);
+    ValT *vb = reinterpret_cast<ValT *>(base + pl.vals_b);
+    int64_t *table = reinterpret_cast<int64_t *>(base + pl.table);
+    void *scan_tmp = base + pl.scan_tmp;
 
     PGLB_CUDA(cudaMemsetAsync(degree, 0, sizeof(int64_t) * N, stream));
     const int blocks = (int)std::min<int64_t>((E + 255) / 256, (int64_t)sm_count() * 16);
     if (E > 0) {
         pack_keys_kernel<KeyT, ValT><<<blocks, 256, 0, stream>>>(
-            u, us, E, keys_in, vals_in, reinterpret_cast<unsigned long long *>(degree));
+            u, us, E, ka, va, reinterpret_cast<unsigned long long *>(degree));
         PGLB_LAUNCH_CHECK("pack_keys_kernel");
     }
     set_first_kernel<<<1, 1, 0, stream>>>(indptr);
     PGLB_LAUNCH_CHECK("set_first_kernel");
     if (N > 0) {
-        size_t tb = pl.scan_tmp_bytes;
-        PGLB_CUDA(cub::DeviceScan::InclusiveSum(base + pl.scan_tmp, tb, degree, indptr + 1, N, stream));
-        count_launch(2);
+        const int rc = scan_i64(degree, indptr + 1, N, /*inclusive=*/1, scan_tmp, stream);
+        if (rc) return rc;
     }
     if (E > 0) {
-        size_t tb = pl.sort_tmp_bytes;
-        PGLB_CUDA(cub::DeviceRadixSort::SortPairs(base + pl.sort_tmp, tb, keys_in, keys_out, vals_in,
-                                                  vals_out, E, 0, key_bits(N), stream));
-        count_launch(4);
-        emit_sorted_kernel<KeyT, ValT><<<blocks, 256, 0, stream>>>(keys_out, vals_out, v, vs, E, su,
-                                                                   sv, se);
+        constexpr int IPW = SortGeo<KeyT>::kIpw;
+        const int bits = key_bits(N);
+        for (int shift = 0; shift < bits; shift += 8) {
+            rs_hist_kernel<KeyT, IPW><<<(unsigned)pl.nb, 256, 0, stream>>>(ka, E, shift, pl.nb, table);
+            PGLB_LAUNCH_CHECK("rs_hist_kernel");
+            const int rc = scan_i64(table, table, 256 * pl.nb, /*inclusive=*/0, scan_tmp, stream);
+            if (rc) return rc;
+            rs_scatter_kernel<KeyT, ValT, IPW><<<(unsigned)pl.nb, 256, 0, stream>>>(ka, va, kb, vb, E, shift,
+                                                                                  pl.nb, table);
+            PGLB_LAUNCH_CHECK("rs_scatter_kernel");
+            std::swap(ka, kb);
+            std::swap(va, vb);
+        }
+        emit_sorted_kernel<KeyT, ValT><<<blocks, 256, 0, stream>>>(ka, va, v, vs, E, su, sv, se);
         PGLB_LAUNCH_CHECK("emit_sorted_kernel");
     }
     return PGLB_OK;
@@ -169,15 +409,8 @@ static bool use_small(int64_t E, int64_t N) { return E < 0xffffffffLL && N < 0xf
 extern "C" int pglb_csr_build_ws(int64_t E, int64_t N, size_t *ws_bytes) {
     PGLB_CHECK_ARG(ws_bytes != nullptr, PGLB_EINVAL, "pglb_csr_build_ws: ws_bytes is NULL");
     PGLB_CHECK_ARG(E >= 0 && N >= 0, PGLB_EINVAL, "pglb_csr_build_ws: negative size");
-    if (use_small(E, N)) {
-        SortPlan<uint32_t, uint32_t> pl;
-        PGLB_CUDA((plan<uint32_t, uint32_t>(E, N, pl)));
-        *ws_bytes = pl.total;
-    } else {
-        SortPlan<uint64_t, uint64_t> pl;
-        PGLB_CUDA((plan<uint64_t, uint64_t>(E, N, pl)));
-        *ws_bytes = pl.total;
-    }
+    *ws_bytes = use_small(E, N) ? plan<uint32_t, uint32_t>(E, N).total
+                                : plan<uint64_t, uint64_t>(E, N).total;
     return PGLB_OK;
 }
 
@@ -204,10 +437,7 @@ extern "C" int pglb_csr_build(const int64_t *u, int64_t u_stride, const int64_t 
 
 extern "C" int pglb_segment_ids_ws(int64_t N, size_t *ws_bytes) {
     PGLB_CHECK_ARG(ws_bytes != nullptr && N >= 0, PGLB_EINVAL, "pglb_segment_ids_ws: bad args");
-    size_t tmp = 0;
-    PGLB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const int64_t *)nullptr,
-                                            (int64_t *)nullptr, N));
-    *ws_bytes = align_up(sizeof(int64_t) * (N ? N : 1), 256) * 2 + align_up(tmp ? tmp : 1, 256);
+    *ws_bytes = align_up(sizeof(int64_t) * (N ? N : 1), 256) * 2 + scan_ws_bytes(N);
     return PGLB_OK;
 }
 
@@ -233,12 +463,13 @@ extern "C" int pglb_segment_ids(const int64_t *indptr, int64_t N, int64_t E, int
     int64_t *flag = reinterpret_cast<int64_t *>(base);
     int64_t *rank = reinterpret_cast<int64_t *>(base + a);
     void *tmp = base + 2 * a;
-    size_t tmp_bytes = ws_bytes - 2 * a;
     const int blocks = (int)std::min<int64_t>((N + 255) / 256, (int64_t)sm_count() * 16);
     nonempty_flag_kernel<<<blocks, 256, 0, stream>>>(indptr, N, flag);
     PGLB_LAUNCH_CHECK("nonempty_flag_kernel");
-    PGLB_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, rank, N, stream));
-    count_launch(2);
+    {
+        const int rc2 = scan_i64(flag, rank, N, /*inclusive=*/0, tmp, stream);
+        if (rc2) return rc2;
+    }
     const int wblocks = (int)std::min<int64_t>((N + 7) / 8, (int64_t)sm_count() * 16);
     emit_segments_kernel<<<wblocks, 256, 0, stream>>>(indptr, rank, N, uniq_ind, segment_ids,
                                                       num_uniq);

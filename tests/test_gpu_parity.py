@@ -792,7 +792,8 @@ def test_lazy_message_fusion(pgl):
     out2 = g.recv(lambda m: m.reduce_sum(m["h"] * 2.0), msg).cpu().numpy()
     assert rel_err(out2, 2 * O.send_u_recv(x, edges[:, 0], edges[:, 1], "sum")) <= RTOL
     assert (msg["h"].cpu().numpy() == x[edges[:, 0]]).all()
-    assert fused_launches <= 4 * 10
+    # a handful of small launches per recv (plan, reduce, fix-up, empty rows, segment-id scan)
+    assert fused_launches <= 4 * 12
 
 
 def test_udf_path_backward(pgl):
