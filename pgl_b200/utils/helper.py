@@ -72,3 +72,23 @@ def scatter(x, index, updates, overwrite=True, name=None):
     out.index_fill_(0, index, 0)
     out.index_add_(0, index, updates)
     return out
+
+
+def graph_send_recv(x, src_index, dst_index, pool_type="sum"):
+    """reference pgl/utils/helper.py:163-210: copy-source send + built-in reduce on a bare COO
+    edge list (out rows = x rows).  The reference gathers [E, D] and scatter-adds it (sum only);
+    here the dst-CSR is built on the device (stable, so the per-row order is edge order) and the
+    fused aggregation kernel runs on it -- mean / max / min come with it.  Nothing is cached:
+    callers that reuse the edge list should hold a Graph instead."""
+    assert pool_type in ("sum", "mean", "max", "min"), \
+        "Only support 'sum', 'mean', 'max', 'min' pool_type."
+    ops.require_cuda(x, src_index, dst_index)
+    n = int(x.shape[0])
+    degree, cols, _, eid, indptr = ops.csr_build(dst_index, src_index, n)
+    fwd = {"indptr": indptr, "cols": cols, "eid": eid, "degree": degree, "max_degree": -1}
+    bwd = None
+    if x.requires_grad and torch.is_grad_enabled():
+        def bwd():
+            d2, c2, _, e2, ip2 = ops.csr_build(src_index, dst_index, n)
+            return {"indptr": ip2, "cols": c2, "eid": e2, "degree": d2, "max_degree": -1}
+    return ops.aggregate_copy(x, fwd, n, pool_type, bwd=bwd)

@@ -107,3 +107,29 @@ def test_bench_reference_arm_contract():
     r2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference"],
                         capture_output=True, text=True, timeout=120, env=dict(os.environ, RANK="1", CUDA_VISIBLE_DEVICES=""))
     assert r2.returncode == 0 and r2.stdout.strip() == ""
+
+
+def test_bigraph_host_mode():
+    """BiGraph in numpy mode: indexes come from the host build (twin of the reference's Cython
+    build_index), degrees / sorted_edges follow reference bigraph.py:594-681, message passing
+    refuses to run until .tensor() (bigraph.py:1157,1181)."""
+    import pgl_b200 as pgl
+    edges = np.array([[0, 1], [2, 0], [2, 1], [1, 1], [3, 0]], np.int64)
+    g = pgl.BiGraph(edges)
+    assert not g.is_tensor() and int(g.src_num_nodes) == 4 and int(g.dst_num_nodes) == 2
+    assert g.indegree().tolist() == [2, 3] and g.outdegree().tolist() == [1, 1, 2, 1]
+    assert g.indegree([1]).tolist() == [3]
+    src, dst, eid = g.sorted_edges("dst")
+    assert dst.tolist() == [0, 0, 1, 1, 1] and eid.tolist() == [1, 4, 0, 2, 3]
+    assert src.tolist() == [2, 3, 0, 2, 1]
+    src, dst, eid = g.sorted_edges("src")
+    assert src.tolist() == [0, 1, 2, 2, 3] and eid.tolist() == [0, 3, 1, 2, 4]
+    assert g.src_nodes.tolist() == [0, 1, 2, 3] and g.dst_nodes.tolist() == [0, 1]
+    with pytest.raises(ValueError):
+        g.sorted_edges("both")
+    with pytest.raises(ValueError):
+        g.send(lambda s, d, e: {}, src_feat={})
+    with pytest.raises(ValueError):
+        g.recv(lambda m: m, {})
+    g2 = pgl.BiGraph(edges, src_num_nodes=6, dst_num_nodes=5)
+    assert len(g2.indegree()) == 5 and len(g2.outdegree()) == 6
