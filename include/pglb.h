@@ -214,6 +214,15 @@ int pglb_gat_fused_csr_f32(const int64_t *indptr, const int64_t *cols, const flo
                            float *out, int64_t ldo, int64_t n_dst, int64_t n_src, int64_t num_edges,
                            int64_t H, int64_t head_dim, void *ws, size_t ws_bytes, void *stream);
 
+/* out[M, N] = act(x[M, K] @ w[K, N] + bias[N]) -- the dense transform of the conv layers
+ * (pgl/nn/conv.py:238-251 GCNConv: `self.linear(...)`, `+ self.bias`, activation; the same Linear in
+ * GATConv :321 / GraphSageConv :107-108) on the tensor cores with 3xTF32 error compensation (fp32-level
+ * accuracy, fp32 accumulate), bias and ReLU fused into the single write of out.
+ * w is contiguous [K, N] (paddle.nn.Linear layout); K % 4 == 0, 4 <= K <= 128; N in {64, 128};
+ * ldx % 4 == 0, x 16-byte aligned; bias may be NULL; act: 0 none, 1 relu. */
+int pglb_linear_tf32x3_f32(const float *x, int64_t ldx, const float *w, const float *bias, float *out,
+                           int64_t ldo, int64_t M, int64_t K, int64_t N, int act, void *stream);
+
 /* norm[i] = clip(float(degree[i]), 1)^-0.5 ; GF.degree_norm (graph_op.py:46-55) */
 int pglb_degree_norm_f32(const int64_t *degree, int64_t n, float *norm, void *stream);
 

@@ -29,10 +29,17 @@ class Linear(nn.Module):
         bound = _math.sqrt(6.0 / (in_features + out_features))  # paddle default: Xavier uniform
         nn.init.uniform_(self.weight, -bound, bound)
 
-    def forward(self, x):
+    def forward(self, x, act=None):
+        """act (None | "relu") is applied after the bias; on the tensor-core path it is fused into
+        the GEMM epilogue (ops.linear_tc), elsewhere it is a separate op."""
+        from .. import ops
+        if ops.linear_tc_ok(x, self.weight):
+            return ops.linear_tc(x, self.weight, self.bias, act)
         y = x @ self.weight
         if self.bias is not None:
             y = y + self.bias
+        if act == "relu":
+            y = F.relu(y)
         return y
 
 
@@ -120,6 +127,15 @@ class GCNConv(nn.Module):
             nv = norm.reshape(-1)
             output = graph._send_u_recv(feature, "sum", None, scale_src=nv, scale_dst=nv)
             if self.input_size <= self.output_size:
+                from .. import ops
+                if ops.linear_tc_ok(output, self.linear.weight):
+                    # 3xTF32 tensor-core GEMM with bias + ReLU in its epilogue: one read, one write
+                    relu = self.activation is F.relu
+                    output = ops.linear_tc(output, self.linear.weight, self.bias,
+                                           "relu" if relu else None)
+                    if self.activation is not None and not relu:
+                        output = self.activation(output)
+                    return output
                 output = torch.addmm(self.bias, output, self.linear.weight)
             else:
                 output = output + self.bias

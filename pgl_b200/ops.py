@@ -796,6 +796,69 @@ def aggregate_ue_slots(x, y_slots, fwd, n_dst, message_op="mul", reduce_op="sum"
     return out.reshape((n_dst,) + out_feat)
 
 
+TC_GEMM = os.environ.get("PGLB_TC_GEMM", "1") != "0"
+TC_GEMM_MIN_ROWS = int(os.environ.get("PGLB_TC_GEMM_MIN_ROWS", "4096"))
+
+
+def linear_tc_ok(x, weight):
+    """True when x @ weight can run on pglb_linear_tf32x3_f32 (tall-skinny fp32, K <= 128 and
+    N in {64, 128}); small or odd shapes stay on torch.matmul (cuBLAS), which is plumbing here."""
+    if not TC_GEMM or not x.is_cuda or x.dim() != 2 or x.dtype != torch.float32 \
+            or weight.dtype != torch.float32:
+        return False
+    M, K = int(x.shape[0]), int(x.shape[1])
+    N = int(weight.shape[1])
+    return M >= TC_GEMM_MIN_ROWS and K % 4 == 0 and 4 <= K <= 128 and N in (64, 128) \
+        and int(weight.shape[0]) == K
+
+
+def _linear_tc_raw(x, weight, bias, act):
+    x2 = x if (x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0) \
+        else x.contiguous()
+    w = weight.contiguous()
+    M, K = int(x2.shape[0]), int(x2.shape[1])
+    N = int(w.shape[1])
+    out = torch.empty((M, N), dtype=torch.float32, device=x2.device)
+    b = bias.contiguous() if bias is not None else None
+    with torch.cuda.device(x2.device):
+        check(lib.pglb_linear_tf32x3_f32(_ptr(x2), x2.stride(0), _ptr(w), _ptr(b) if b is not None else None,
+                                         _ptr(out), N, M, K, N, 1 if act == "relu" else 0, _stream()))
+    return out
+
+
+class _LinearTC(torch.autograd.Function):
+    """Forward on the 3xTF32 tensor-core kernel (bias + ReLU fused); backward is two plain fp32
+    matmuls (training plumbing: the reference gets them from Paddle autograd)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        out = _linear_tc_raw(x, weight, bias, act)
+        ctx.act = act
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight, out if act == "relu" else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, out = ctx.saved_tensors
+        if ctx.act == "relu":
+            g = g * (out > 0)
+        gx = g @ weight.t() if ctx.needs_input_grad[0] else None
+        gw = x.t() @ g if ctx.needs_input_grad[1] else None
+        gb = g.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb, None
+
+
+def linear_tc(x, weight, bias=None, act=None):
+    """act(x @ weight + bias) with weight [in, out]; act in (None, "relu")."""
+    require_cuda(x, weight)
+    assert act in (None, "relu")
+    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad
+                                    or (bias is not None and bias.requires_grad)):
+        return _LinearTC.apply(x, weight, bias, act)
+    return _linear_tc_raw(x, weight, bias, act)
+
+
 def degree_norm(degree):
     require_cuda(degree)
     degree = _i64(degree).contiguous()
