@@ -13,7 +13,7 @@ Prints ONE JSON line (rank 0).  Keys follow the driver contract; additionally
   roofline      dominant kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json)
   cpu_baseline  the oracle's C restatement of the reference CPU loop on a bounded sample
   e2e           same metric through the public API with pinned HOST buffers (H2D + D2H inside)
-  full_layer    GCNConv(128,128).forward (aggregation + fp32 GEMM + bias + ReLU) edges/s
+  full_layer    GCNConv(128,128).forward (aggregation + 3xTF32 GEMM + bias + ReLU) edges/s
 """
 import argparse
 import ctypes
@@ -435,7 +435,8 @@ def main_ours(args):
                      "kernel_ms_p90": per[(len(per) * 9) // 10]},
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "full_layer": {"value": e / (full_ms * 1e-3), "unit": "edges/s", "ms": full_ms,
-                       "what": "GCNConv(128,128,relu).forward: aggregation + fp32 addmm + ReLU"},
+                       "what": "GCNConv(128,128,relu).forward: aggregation + 3xTF32 tensor-core GEMM "
+                               "with bias + ReLU in its epilogue (PGLB_TC_GEMM=0: fp32 addmm + ReLU)"},
     }
     print(json.dumps(result))
 

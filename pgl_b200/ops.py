@@ -49,7 +49,12 @@ def _i64(t):
 
 
 def _f32_2d(t):
-    """[n, d1, d2, ...] -> contiguous [n, D] float32 view (no copy when already so)."""
+    """[n, d1, d2, ...] -> contiguous [n, D] float32 view (no copy when already so).  A lazy row
+    gather (utils.op.LazyRows) is resolved to its plain tensor first: the wrapper itself carries no
+    autograd state, so requires_grad must be read from the gathered result."""
+    mat = getattr(t, "materialize", None)
+    if mat is not None:
+        t = mat()
     if t.dtype != torch.float32:
         raise TypeError("pgl_b200: float32 features expected on the CUDA path, got %s" % t.dtype)
     t2 = t.reshape(t.shape[0], -1) if t.dim() != 2 else t
