@@ -12,14 +12,16 @@
 // Not the tcgen05 path: the operands need the hi/lo split in registers between the load and the MMA,
 // and at 1 TFLOP of TF32 work per layer against 10 GB of traffic the legacy warp-level MMA is already
 // within a small factor of the HBM bound; a tcgen05/TMEM version is listed in DESIGN.md as next.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
 
 namespace pglb {
 
-constexpr int LT_ROWS = 64;        // rows of x per tile
-constexpr int LT_THREADS = 256;    // 8 warps: 4 row blocks of 16 x 2 column halves
+constexpr int LT_ROWS = 64;        // rows of x per tile: 4 row blocks of 16
+constexpr int LT_WARPS_DEFAULT = 8;  // 8 warps = 4 row blocks x 2 column groups; 16 = 4 x 4
 constexpr int LT_KMAX = 128;
 constexpr int LT_XS = LT_KMAX + 4;  // x tile row stride (floats): 132 = 4 mod 32 -> conflict-free A loads
 
@@ -46,13 +48,16 @@ __device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, i
 // N = output width (64 or 128).  Dynamic shared memory:
 //   W2 [LT_KMAX][N + 4] of {hi, lo} tf32 pairs (rows >= K are zero)
 //   X  [2][LT_ROWS][LT_XS] fp32 (columns >= K stay zero)
-template <int N>
-__global__ void __launch_bounds__(LT_THREADS, 1)
+template <int N, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
 linear_tf32x3_kernel(const float *__restrict__ x, int64_t ldx, const float *__restrict__ w,
                      const float *__restrict__ bias, float *__restrict__ out, int64_t ldo, int64_t M,
                      int K, int act) {
     constexpr int WS = N + 4;    // W2 row stride in pairs: (N+4) = 4 mod 16 -> conflict-free LDS.64
-    constexpr int NT = N / 16;   // 8-wide column tiles per warp (each warp owns N/2 columns)
+    constexpr int LT_THREADS = WARPS * 32;
+    constexpr int CG = WARPS / 4;    // column groups
+    constexpr int WCOLS = N / CG;    // columns owned by one warp
+    constexpr int NT = WCOLS / 8;    // 8-wide column tiles per warp
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint2 *W2 = reinterpret_cast<uint2 *>(smem_raw);
     float *X = reinterpret_cast<float *>(smem_raw + sizeof(uint2) * LT_KMAX * WS);
@@ -122,7 +127,7 @@ linear_tf32x3_kernel(const float *__restrict__ x, int64_t ldx, const float *__re
                 alo[i] = to_tf32(af[i] - __uint_as_float(ahi[i]));
             }
             uint2 b0[NT], b1[NT];
-            const uint2 *wr0 = W2 + (k0 + t) * WS + wn * (N / 2) + g;
+            const uint2 *wr0 = W2 + (k0 + t) * WS + wn * WCOLS + g;
             const uint2 *wr1 = wr0 + 4 * WS;
 #pragma unroll
             for (int j = 0; j < NT; ++j) {
@@ -142,7 +147,7 @@ linear_tf32x3_kernel(const float *__restrict__ x, int64_t ldx, const float *__re
         const int64_t row0 = tile * LT_ROWS + wm * 16 + g;
 #pragma unroll
         for (int j = 0; j < NT; ++j) {
-            const int col = wn * (N / 2) + j * 8 + 2 * t;
+            const int col = wn * WCOLS + j * 8 + 2 * t;
             float bx = 0.f, by = 0.f;
             if (bias) {
                 bx = __ldg(bias + col);
@@ -163,19 +168,19 @@ linear_tf32x3_kernel(const float *__restrict__ x, int64_t ldx, const float *__re
     }
 }
 
-template <int N>
+template <int N, int WARPS>
 static int launch(const float *x, int64_t ldx, const float *w, const float *bias, float *out,
                   int64_t ldo, int64_t M, int K, int act, cudaStream_t stream) {
     const size_t smem = sizeof(uint2) * LT_KMAX * (N + 4) + sizeof(float) * 2 * LT_ROWS * LT_XS;
     static bool configured = false;
     if (!configured) {
-        PGLB_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<N>,
+        PGLB_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<N, WARPS>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     const int64_t tiles = (M + LT_ROWS - 1) / LT_ROWS;
     const unsigned grid = (unsigned)std::min<int64_t>(tiles, sm_count());
-    linear_tf32x3_kernel<N><<<grid, LT_THREADS, smem, stream>>>(x, ldx, w, bias, out, ldo, M, K, act);
+    linear_tf32x3_kernel<N, WARPS><<<grid, WARPS * 32, smem, stream>>>(x, ldx, w, bias, out, ldo, M, K, act);
     PGLB_LAUNCH_CHECK("linear_tf32x3_kernel");
     return PGLB_OK;
 }
@@ -199,6 +204,15 @@ extern "C" int pglb_linear_tf32x3_f32(const float *x, int64_t ldx, const float *
     PGLB_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 8) == 0, PGLB_EINVAL,
                    "pglb_linear_tf32x3_f32: x must be 16-byte and out 8-byte aligned");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    if (N == 128) return launch<128>(x, ldx, w, bias, out, ldo, M, (int)K, act, s);
-    return launch<64>(x, ldx, w, bias, out, ldo, M, (int)K, act, s);
+    // PGLB_LINEAR_WARPS = 8 | 16 picks the CTA shape (tuning knob; both are covered by the tests)
+    int warps = LT_WARPS_DEFAULT;
+    if (const char *e = getenv("PGLB_LINEAR_WARPS")) {
+        const int v = atoi(e);
+        if (v == 8 || v == 16) warps = v;
+    }
+    if (N == 128)
+        return warps == 16 ? launch<128, 16>(x, ldx, w, bias, out, ldo, M, (int)K, act, s)
+                           : launch<128, 8>(x, ldx, w, bias, out, ldo, M, (int)K, act, s);
+    return warps == 16 ? launch<64, 16>(x, ldx, w, bias, out, ldo, M, (int)K, act, s)
+                       : launch<64, 8>(x, ldx, w, bias, out, ldo, M, (int)K, act, s);
 }

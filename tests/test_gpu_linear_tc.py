@@ -21,9 +21,11 @@ def rel_err(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-12))
 
 
+@pytest.mark.parametrize("warps", ["8", "16"])
 @pytest.mark.parametrize("M,K,N", [(5000, 128, 128), (4097, 100, 128), (10000, 64, 64), (6401, 8, 64),
                                    (64, 128, 128), (1, 4, 128), (70001, 128, 64)])
-def test_linear_tc_matches_fp64(pgl, M, K, N):
+def test_linear_tc_matches_fp64(pgl, monkeypatch, M, K, N, warps):
+    monkeypatch.setenv("PGLB_LINEAR_WARPS", warps)  # both CTA shapes of the kernel
     gen = torch.Generator(device="cuda").manual_seed(M + K + N)
     x = torch.randn(M, K, device="cuda", generator=gen) * 3
     w = torch.randn(K, N, device="cuda", generator=gen)
