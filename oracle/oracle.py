@@ -444,6 +444,26 @@ def gat_conv(edges, num_nodes, feature, w, b, weight_src, weight_dst, num_heads,
     return _act(out, activation)
 
 
+def load_cora(path):
+    """BASELINE config 2 from the committed fixture tests/golden/cora.npz (made by
+    tests/golden/make_cora.py from the reference's pgl/data/cora with the logic of
+    pgl/dataset.py:195-246).  Returns a dict: num_nodes, edges [E,2] int64, x [N,1433] float32
+    (row-normalised by the dataset, pgl/dataset.py:213, and again by the training script,
+    examples/citation_benchmark/train.py:29-30,44), y, num_classes and the fixed
+    train / val / test index split (dataset.py:240-243)."""
+    z = np.load(path)
+    n, words = int(z["num_nodes"]), int(z["num_words"])
+    x = np.zeros((n, words), np.float32)
+    x[z["feat_row"].astype(np.int64), z["feat_col"].astype(np.int64)] = 1.0
+    x = (x / (x.sum(axis=1, keepdims=True) + np.float32(1e-15))).astype(np.float32)
+    x = (x / np.maximum(x.sum(axis=-1, keepdims=True), 1)).astype(np.float32)
+    perm = np.arange(n)
+    y = z["labels"].astype(np.int64)
+    return {"num_nodes": n, "edges": z["edges"].astype(np.int64), "x": x, "y": y,
+            "num_classes": int(y.max()) + 1, "train_index": perm[:140], "val_index": perm[200:500],
+            "test_index": perm[500:1500]}
+
+
 # --------------------------------------------------------------------------
 # Workload generators shared by tests and bench (SURVEY.md section 8d)
 # --------------------------------------------------------------------------
