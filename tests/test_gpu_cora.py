@@ -79,7 +79,7 @@ def test_cora_training_reaches_published_accuracy(pgl, cora):
         loss.backward()
         optim.step()
         if first_loss is None:
-            first_loss = float(loss)
+            first_loss = float(loss.detach())
         model.eval()
         with torch.no_grad():
             pred = model(g, x).argmax(1)
@@ -88,6 +88,6 @@ def test_cora_training_reaches_published_accuracy(pgl, cora):
         if val > best_val:
             best_val, test_at_best = val, test
     assert pgl.ops.launch_count() - l0 >= 200 * 6  # every aggregation, forward and backward, is ours
-    assert float(loss) < 0.5 * first_loss
+    assert float(loss.detach()) < 0.5 * first_loss
     # published: 0.807 +- 0.010 over 10 runs; one seeded run must land in a generous band around it
     assert 0.77 <= test_at_best <= 0.85, (best_val, test_at_best)
