@@ -38,15 +38,34 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
+
+// SM count of the CURRENT device (cached per device: a process may drive several GPUs).
 inline int sm_count() {
-    static int n = 0;
+    static std::atomic<int> cache[64];
+    const int dev = current_device();
+    int n = cache[dev & 63].load(std::memory_order_relaxed);
     if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        cache[dev & 63].store(n, std::memory_order_relaxed);
     }
     return n;
+}
+
+// Opt a kernel into more than 48 KB of dynamic shared memory.  The attribute is per device, so the
+// "already done" flag is a bit per device (one mask per kernel instantiation, owned by the caller).
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kernel, int bytes, std::atomic<unsigned long long> &done) {
+    const unsigned long long bit = 1ull << (current_device() & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
 }
 
 // ---- device helpers -------------------------------------------------------------------

@@ -172,12 +172,8 @@ template <int N, int WARPS>
 static int launch(const float *x, int64_t ldx, const float *w, const float *bias, float *out,
                   int64_t ldo, int64_t M, int K, int act, cudaStream_t stream) {
     const size_t smem = sizeof(uint2) * LT_KMAX * (N + 4) + sizeof(float) * 2 * LT_ROWS * LT_XS;
-    static bool configured = false;
-    if (!configured) {
-        PGLB_CUDA(cudaFuncSetAttribute(linear_tf32x3_kernel<N, WARPS>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    PGLB_CUDA(ensure_dyn_smem(linear_tf32x3_kernel<N, WARPS>, (int)smem, attr_done));
     const int64_t tiles = (M + LT_ROWS - 1) / LT_ROWS;
     const unsigned grid = (unsigned)std::min<int64_t>(tiles, sm_count());
     linear_tf32x3_kernel<N, WARPS><<<grid, WARPS * 32, smem, stream>>>(x, ldx, w, bias, out, ldo, M, K, act);

@@ -831,12 +831,8 @@ static int launch_stream128_cfg(const StreamP &p, cudaStream_t stream) {
     typedef Geo<CFG, YM> G_;
     constexpr int W = G_::kWarps;
     const int smem = G_::kSmem;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PGLB_CUDA(cudaFuncSetAttribute(spmm_stream128_kernel<RK, SCALED, PK, YM, CFG>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    PGLB_CUDA(ensure_dyn_smem(spmm_stream128_kernel<RK, SCALED, PK, YM, CFG>, smem, attr_done));
     const int64_t blocks = (p.ntasks + W - 1) / W;
     PGLB_CHECK_ARG(blocks <= 0x7fffffffLL, PGLB_ESHAPE, "spmm_stream: grid too large");
     spmm_stream128_kernel<RK, SCALED, PK, YM, CFG><<<(unsigned)blocks, W * 32, smem, stream>>>(p);
@@ -860,12 +856,8 @@ static int launch_stream128(const StreamP &p, cudaStream_t stream) {
 template <int ITERS, int RK>
 static int launch_stream(const StreamP &p, int tiles, cudaStream_t stream) {
     typedef StreamCfg<ITERS> Cfg;
-    static bool attr_set = false;
-    if (!attr_set) {
-        PGLB_CUDA(cudaFuncSetAttribute(spmm_stream_kernel<ITERS, RK>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem));
-        attr_set = true;
-    }
+    static std::atomic<unsigned long long> attr_done{0};
+    PGLB_CUDA(ensure_dyn_smem(spmm_stream_kernel<ITERS, RK>, Cfg::kSmem, attr_done));
     const int64_t blocks = (p.ntasks + Cfg::kWarps - 1) / Cfg::kWarps;
     PGLB_CHECK_ARG(blocks <= 0x7fffffffLL, PGLB_ESHAPE, "spmm_stream: grid too large");
     dim3 grid((unsigned)blocks, (unsigned)tiles);
