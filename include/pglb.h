@@ -223,6 +223,35 @@ int pglb_gat_fused_csr_f32(const int64_t *indptr, const int64_t *cols, const flo
 int pglb_linear_tf32x3_f32(const float *x, int64_t ldx, const float *w, const float *bias, float *out,
                            int64_t ldo, int64_t M, int64_t K, int64_t N, int act, void *stream);
 
+/* ------------------------------------------------------------------------------------
+ * Neighbour sampling + reindex for mini-batch GraphSAGE.  Replace
+ * paddle.geometric.sample_neighbors / reindex_graph as called by NeighborSampler.sample_neighbors
+ * (pgl/sampling/sage.py:130-155) on the cached dst-CSR (row = adj_dst_index._sorted_v,
+ * colptr = adj_dst_index._indptr).  EXPERIMENTAL: not yet validated on hardware (round 1).
+ * ---------------------------------------------------------------------------------- */
+/* count[i] = min(deg(nodes[i]), sample_size)  (all neighbours when sample_size < 0);
+ * offsets[0..n] = exclusive scan of count, offsets[n] = total (n + 1 entries). */
+int pglb_sample_count(const int64_t *indptr, const int64_t *nodes, int64_t n, int64_t sample_size,
+                      int64_t *count, int64_t *offsets, void *stream);
+/* out_neighbors[offsets[i] + j] = j-th sampled in-neighbour of nodes[i]: the whole list in CSR order
+ * when deg <= sample_size, else a uniform subset without replacement (Floyd), a pure function of
+ * (seed, i).  out_eids (may be NULL) receives eid[slot] (or the CSR slot when eid is NULL).
+ * sample_size <= 4096; degrees < 2^31. */
+int pglb_sample_fill(const int64_t *indptr, const int64_t *row, const int64_t *eid, const int64_t *nodes,
+                     int64_t n, int64_t sample_size, uint64_t seed, const int64_t *offsets,
+                     int64_t *out_neighbors, int64_t *out_eids, void *stream);
+/* Dense lookup table for pglb_reindex_graph: num_nodes int64, filled with INT64_MAX ("empty"). */
+int pglb_reindex_table_init(int64_t *table, int64_t num_nodes, void *stream);
+int pglb_reindex_graph_ws(int64_t num_neighbors, size_t *ws_bytes);
+/* paddle.geometric.reindex_graph(x, neighbors, count): out_nodes = x followed by the new ids among
+ * neighbors in first-appearance order; reindex_src[p] = position of neighbors[p] in out_nodes;
+ * reindex_dst[p] = i for the slots of x[i] (offsets as produced by pglb_sample_count, n + 1 entries).
+ * x must hold distinct ids.  *num_out (device scalar) = number of entries written to out_nodes
+ * (capacity n + m).  table: see pglb_reindex_table_init; left all-empty again on return. */
+int pglb_reindex_graph(const int64_t *x, int64_t n, const int64_t *neighbors, const int64_t *offsets,
+                       int64_t m, int64_t *table, int64_t *reindex_src, int64_t *reindex_dst,
+                       int64_t *out_nodes, int64_t *num_out, void *ws, size_t ws_bytes, void *stream);
+
 /* norm[i] = clip(float(degree[i]), 1)^-0.5 ; GF.degree_norm (graph_op.py:46-55) */
 int pglb_degree_norm_f32(const int64_t *degree, int64_t n, float *norm, void *stream);
 

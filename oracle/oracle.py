@@ -444,6 +444,56 @@ def gat_conv(edges, num_nodes, feature, w, b, weight_src, weight_dst, num_heads,
     return _act(out, activation)
 
 
+def reindex_graph(x, neighbors, count):
+    """paddle.geometric.reindex_graph as the reference's GPU sampler uses it
+    (pgl/sampling/sage.py:146-147): out_nodes = x followed by the ids of ``neighbors`` not in x, in
+    first-appearance order; reindex_src = neighbors mapped to positions in out_nodes; reindex_dst =
+    position of the owning x entry, repeated count[i] times.  Pinned by the example in Paddle's API
+    reference (x=[0,1,2], neighbors=[8,9,0,4,7,6,7], count=[2,3,2])."""
+    x = np.asarray(x, np.int64).reshape(-1)
+    neighbors = np.asarray(neighbors, np.int64).reshape(-1)
+    count = np.asarray(count, np.int64).reshape(-1)
+    pos = {int(v): i for i, v in enumerate(x)}
+    out_nodes = [int(v) for v in x]
+    src = np.empty(len(neighbors), np.int64)
+    for p, v in enumerate(neighbors):
+        v = int(v)
+        if v not in pos:
+            pos[v] = len(out_nodes)
+            out_nodes.append(v)
+        src[p] = pos[v]
+    dst = np.repeat(np.arange(len(x), dtype=np.int64), count)
+    return src, dst, np.asarray(out_nodes, np.int64)
+
+
+def check_sampled_neighbors(indptr, row, nodes, sample_size, neighbors, count):
+    """Properties every valid output of paddle.geometric.sample_neighbors has (the draw itself is
+    random): count = min(deg, k) (deg when k < 0), whole list in order when deg <= k, otherwise a
+    sub-multiset of the neighbour list (no slot used twice).  Returns None or a message."""
+    indptr, row = np.asarray(indptr), np.asarray(row)
+    o = 0
+    for i, v in enumerate(np.asarray(nodes).reshape(-1)):
+        lst = row[indptr[v]:indptr[v + 1]]
+        deg = len(lst)
+        want = deg if (sample_size < 0 or deg <= sample_size) else sample_size
+        if int(count[i]) != want:
+            return "count[%d] = %d, expected %d" % (i, int(count[i]), want)
+        got = np.asarray(neighbors[o:o + want])
+        if want == deg:
+            if not (got == lst).all():
+                return "node %d: full list expected in CSR order" % int(v)
+        else:
+            a, ca = np.unique(got, return_counts=True)
+            b, cb = np.unique(lst, return_counts=True)
+            m = dict(zip(b.tolist(), cb.tolist()))
+            if any(m.get(int(t), 0) < int(c) for t, c in zip(a, ca)):
+                return "node %d: sample is not a sub-multiset of its neighbour list" % int(v)
+        o += want
+    if o != len(neighbors):
+        return "neighbors has %d entries, counts add up to %d" % (len(neighbors), o)
+    return None
+
+
 def load_cora(path):
     """BASELINE config 2 from the committed fixture tests/golden/cora.npz (made by
     tests/golden/make_cora.py from the reference's pgl/data/cora with the logic of
