@@ -426,6 +426,8 @@ int gat_fused_run(const int64_t *indptr, const int64_t *cols, const float *f, in
                   const float *attn_src, const float *attn_dst, float slope, void *ws, size_t ws_bytes,
                   cudaStream_t stream);
 
+bool stream_narrow_enabled();  // PGLB_NARROW=1: experimental narrow-row streaming kernel (spmm_stream.cu)
+
 static bool use_stream_path() {
     static int v = -1;
     if (v < 0) {
@@ -490,7 +492,8 @@ extern "C" int pglb_spmm_csr_f32(const int64_t *indptr, const int64_t *cols, con
     const bool ue_fast = mode == 1 && D <= 128 && scale_src == nullptr && num_edges < 0x7fffffffLL &&
                          (msg_op == PGLB_MSG_MUL || msg_op == PGLB_MSG_ADD) &&
                          (y_bcast == PGLB_BCAST_SCALAR || (y_bcast == PGLB_BCAST_HEAD && head_dim % 4 == 0));
-    if ((mode == 0 || ue_fast) && vec4 && D > 64 && num_edges > 0 && use_stream_path()) {
+    const bool narrow = mode == 0 && D <= 64 && reduce_op < PGLB_REDUCE_MAX && stream_narrow_enabled();
+    if ((mode == 0 || ue_fast) && vec4 && (D > 64 || narrow) && num_edges > 0 && use_stream_path()) {
         PGLB_CHECK_ARG((reinterpret_cast<uintptr_t>(ws) & 255u) == 0, PGLB_EWORKSPACE,
                        "pglb_spmm_csr_f32: workspace must be 256-byte aligned");
         return spmm_stream_run(indptr, cols, x, ldx, out, ldo, n_dst, n_src, num_edges, D,

@@ -15,4 +15,5 @@ aggregation it fetches just the distinct remote source rows it needs ("halo").
                     (``mode="p2p"``).
 """
 from .halo import HaloPlan, block_offsets, relabel_by_partition  # noqa: F401
+from .colshard import ColumnShardedGraph  # noqa: F401
 from .sharded import ShardedGraph  # noqa: F401

@@ -346,12 +346,17 @@ class _MaxMinAgg(torch.autograd.Function):
         return gx, None, None, None, None
 
 
+# PGLB_NARROW=1 (experimental): rows of <= 64 floats take the narrow-row streaming kernel, which reads
+# packed column ids like the wide-row kernel
+NARROW_ROWS = os.environ.get("PGLB_NARROW") == "1"
+
+
 def _packed_of(csr, x2):
     """Packed column ids (+ optional L2 hints) for this (graph, row width), from the EdgeIndex
     cache; only the wide-row kernel (64 < D <= 128) consumes them."""
     fn = csr.get("packed")
     D = int(x2.shape[1])
-    if fn is None or D <= 64 or D > 128 or D % 4:
+    if fn is None or D > 128 or D % 4 or (D <= 64 and not NARROW_ROWS):
         return None
     return fn(int(x2.shape[0]), D * 4)
 
