@@ -61,8 +61,8 @@ def reindex_graph(x, neighbors, count, num_nodes=None):
     lookup table, cached per device); default max id + 1."""
     ops.require_cuda(x, neighbors, count)
     x = x.reshape(-1).to(torch.int64).contiguous()
+    offsets = getattr(neighbors, "_pglb_offsets", None)  # set by sample_neighbors (saves a scan)
     neighbors = neighbors.reshape(-1)
-    offsets = getattr(neighbors, "_pglb_offsets", None)
     nb = neighbors.to(torch.int64).contiguous()
     n, m = int(x.shape[0]), int(nb.shape[0])
     dev = x.device
