@@ -50,6 +50,31 @@ def parse():
     return ap.parse_args()
 
 
+def host_threads():
+    """CPU threads this process may really use: the affinity mask, capped by a cgroup CPU quota if
+    one is set (os.cpu_count() reports the machine, not the container)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()           # cgroup v2: "<quota|max> <period>"
+        if q[0] != "max":
+            quota = int(q[0]) / int(q[1])
+    except Exception:
+        try:                                                           # cgroup v1
+            cq = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            cp = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if cq > 0 and cp > 0:
+                quota = cq / cp
+        except Exception:
+            pass
+    if quota is not None:
+        n = min(n, max(1, int(quota + 0.999)))
+    return max(1, n)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -212,7 +237,7 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     edges = gen_edges(torch, args.nodes, args.edges, args.exponent, args.seed, dev)
     edges_np = edges.cpu().numpy()
@@ -412,7 +437,7 @@ def main_ours(args):
         try:
             edges_np = edges.cpu().numpy()
             x_np = x_host.numpy() if x_host is not None else x.cpu().numpy()
-            info = run_cpu_reference(edges_np, x_np, n, d, threads=os.cpu_count() or 1, target_s=12.0)
+            info = run_cpu_reference(edges_np, x_np, n, d, threads=host_threads(), target_s=12.0)
             cpu = {"value": info["coo_1thread"]["edges_per_s"], "unit": "edges/s", "cores": 1,
                    "kind": "port", "sample": info["sample"], "detail": info}
         except Exception as ex:
