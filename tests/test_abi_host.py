@@ -137,3 +137,34 @@ def test_tensor_mode_requires_cuda():
         g.tensor()
     with pytest.raises(RuntimeError, match="CUDA"):
         pgl.ops.aggregate_copy(torch.zeros(2, 4), {}, 2)
+
+
+def test_argument_validation_of_the_newer_entries():
+    """Dense transform, sampling and reindex entries: shapes and pointers are checked before any
+    device work, zero-sized problems are no-ops (no GPU needed for either)."""
+    from pgl_b200 import _lib
+    lib = _lib.lib
+    one = ctypes.c_void_p(16)   # a non-NULL, 16-byte aligned dummy: must never be dereferenced here
+    # pglb_linear_tf32x3_f32(x, ldx, w, bias, out, ldo, M, K, N, act, stream)
+    assert lib.pglb_linear_tf32x3_f32(None, 128, None, None, None, 128, 0, 128, 128, 0, None) == 0
+    assert lib.pglb_linear_tf32x3_f32(one, 130, one, None, one, 128, 10, 130, 128, 0, None) < 0
+    assert b"K must be" in lib.pglb_last_error()
+    assert lib.pglb_linear_tf32x3_f32(one, 128, one, None, one, 96, 10, 128, 96, 0, None) < 0
+    assert b"N must be" in lib.pglb_last_error()
+    assert lib.pglb_linear_tf32x3_f32(one, 128, one, None, one, 128, 10, 128, 128, 7, None) < 0
+    assert lib.pglb_linear_tf32x3_f32(None, 128, one, None, one, 128, 10, 128, 128, 0, None) < 0
+    assert lib.pglb_linear_tf32x3_f32(one, 126, one, None, one, 128, 10, 124, 128, 0, None) < 0  # ldx % 4
+    # sampling
+    assert lib.pglb_sample_fill(None, None, None, None, 0, 5, 1, None, None, None, None) == 0
+    assert lib.pglb_sample_fill(one, one, None, one, 3, 5000, 1, one, one, None, None) < 0
+    assert b"4096" in lib.pglb_last_error()
+    assert lib.pglb_sample_fill(None, one, None, one, 3, 5, 1, one, one, None, None) < 0
+    assert lib.pglb_sample_count(None, None, -1, 5, None, one, None) < 0
+    # reindex
+    need = ctypes.c_size_t(0)
+    assert lib.pglb_reindex_graph_ws(1000, ctypes.byref(need)) == 0 and need.value >= 2 * 8 * 1000
+    assert lib.pglb_reindex_graph_ws(-1, ctypes.byref(need)) < 0
+    assert lib.pglb_reindex_table_init(None, 0, None) == 0
+    assert lib.pglb_reindex_table_init(None, 10, None) < 0
+    assert lib.pglb_reindex_graph(one, 3, one, one, 5, one, one, one, one, one, one, 8, None) < 0
+    assert b"workspace" in lib.pglb_last_error()
