@@ -74,3 +74,22 @@ class ColumnShardedGraph(object):
     def gcn_aggregate(self, x_cols, norm):
         nv = norm.reshape(-1)
         return self.send_recv(x_cols, "sum", scale_src=nv, scale_dst=nv)
+
+    def gcn_layer(self, x_cols, norm, weight, bias=None, activation=None, aggregate=None):
+        """One GCNConv layer (reference pgl/nn/conv.py:218-254, aggregate-then-transform order) on the
+        column-sharded layout: aggregate my columns (no exchange) -> all-to-all to whole rows ->
+        dense transform of my row block -> all-to-all back to columns.  ``weight`` is the full
+        [D, D_out] matrix (replicated; D_out divisible by the world size).  Returns [N, D_out / R].
+        ``aggregate(x_cols, norm)`` can be injected (the gloo test passes the oracle)."""
+        n = int(x_cols.shape[0])
+        agg = (aggregate or self.gcn_aggregate)(x_cols, norm)
+        rows = self.to_rows(agg)
+        out = rows @ weight
+        if bias is not None:
+            out = out + bias
+        if activation is not None:
+            out = activation(out)
+        d_out = int(weight.shape[1])
+        assert d_out % self.world == 0
+        back = ColumnShardedGraph(None, d_out, self.world, self.rank, self.group)
+        return back.to_cols(out, n)

@@ -140,6 +140,20 @@ def _colshard_worker(rank, world, port, n, ret):
         full = O.send_u_recv(x, edges[:, 0], edges[:, 1], "sum")
         mine = O.send_u_recv(x[:, lo:hi], edges[:, 0], edges[:, 1], "sum")
         np.testing.assert_array_equal(mine, full[:, lo:hi])
+        # a whole GCN layer on the column-sharded layout == the oracle's layer, column slice by slice
+        w = (rng.standard_normal((d, 6)) * 0.3).astype(np.float32)
+        bias = rng.standard_normal(6).astype(np.float32)
+        norm = O.degree_norm(O.adj_dst_index(edges, n)[0], np.float32)
+
+        def oracle_agg(xc, nrm):
+            xs = xc.numpy() * nrm
+            return torch.from_numpy(O.send_u_recv(xs, edges[:, 0], edges[:, 1], "sum") * nrm)
+
+        got = cs.gcn_layer(x_cols, norm, torch.from_numpy(w), torch.from_numpy(bias), torch.relu,
+                           aggregate=oracle_agg)
+        want = O.gcn_conv(edges, n, x, w, bias, activation="relu")
+        olo, ohi = rank * 6 // world, (rank + 1) * 6 // world
+        np.testing.assert_allclose(got.numpy(), want[:, olo:ohi], rtol=1e-5, atol=1e-5)
         ret[rank] = "ok"
     except Exception:  # pragma: no cover
         import traceback
