@@ -252,6 +252,13 @@ int pglb_reindex_graph(const int64_t *x, int64_t n, const int64_t *neighbors, co
                        int64_t m, int64_t *table, int64_t *reindex_src, int64_t *reindex_dst,
                        int64_t *out_nodes, int64_t *num_out, void *ws, size_t ws_bytes, void *stream);
 
+/* Same contract as pglb_memcpy2d_async, but the copy is done by a kernel through the unified address
+ * space (zero-copy loads / stores across PCIe; the host side must be pinned memory).  For narrow column
+ * blocks, where the copy engine's 2-D transfers run at about half the PCIe rate.  width, pitches and both
+ * pointers multiples of 16 bytes; ctas <= 0 -> 16.  EXPERIMENTAL: not yet run on hardware (round 1). */
+int pglb_copy2d_kernel_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes,
+                             int64_t height, int ctas, void *stream);
+
 /* norm[i] = clip(float(degree[i]), 1)^-0.5 ; GF.degree_norm (graph_op.py:46-55) */
 int pglb_degree_norm_f32(const int64_t *degree, int64_t n, float *norm, void *stream);
 

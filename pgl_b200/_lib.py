@@ -64,6 +64,7 @@ _SIGS = {
     "pglb_reindex_table_init": (c_int, [_p, _i64, _p]),
     "pglb_reindex_graph_ws": (c_int, [_i64, POINTER(c_size_t)]),
     "pglb_reindex_graph": (c_int, [_p, _i64, _p, _p, _i64, _p, _p, _p, _p, _p, _p, c_size_t, _p]),
+    "pglb_copy2d_kernel_async": (c_int, [_p, c_size_t, _p, c_size_t, c_size_t, _i64, c_int, _p]),
     "pglb_linear_tf32x3_f32": (c_int, [_p, _i64, _p, _p, _p, _i64, _i64, _i64, _i64, c_int, _p]),
     "pglb_gat_fused_csr_f32": (c_int, [_p, _p, _p, _i64, _p, _p, ctypes.c_float, _p, _i64, _i64, _i64, _i64,
                                        _i64, _i64, _p, c_size_t, _p]),

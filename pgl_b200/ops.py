@@ -153,6 +153,22 @@ def _spmm_raw(indptr, cols, x2, n_dst, reduce_op, eid=None, y2=None, y_bcast=BCA
     return out
 
 
+# PGLB_HOST_COPY=kernel (experimental): move the column blocks of HostAggregator with a zero-copy kernel
+# instead of cudaMemcpy2DAsync (csrc/host_copy.cu); PGLB_HOST_COPY_CTAS sets its grid (default 16)
+HOST_COPY_KERNEL = os.environ.get("PGLB_HOST_COPY") == "kernel"
+HOST_COPY_CTAS = int(os.environ.get("PGLB_HOST_COPY_CTAS", "16"))
+
+
+def _copy2d(dst_ptr, dpitch, src_ptr, spitch, width, height, kind, stream):
+    """kind 1: host -> device, 2: device -> host (pglb_memcpy2d_async's convention)."""
+    if HOST_COPY_KERNEL:
+        check(lib.pglb_copy2d_kernel_async(ctypes.c_void_p(dst_ptr), dpitch, ctypes.c_void_p(src_ptr), spitch,
+                                           width, height, HOST_COPY_CTAS, ctypes.c_void_p(stream)))
+    else:
+        check(lib.pglb_memcpy2d_async(ctypes.c_void_p(dst_ptr), dpitch, ctypes.c_void_p(src_ptr), spitch,
+                                      width, height, kind, ctypes.c_void_p(stream)))
+
+
 class HostAggregator(object):
     """send_u_recv for features that live in (pinned) HOST memory: out_host = aggregate(x_host).
 
@@ -185,10 +201,8 @@ class HostAggregator(object):
         ev_in, ev_done = [], []
         with torch.cuda.device(self.device):
             for lo, hi in self.bounds:
-                check(lib.pglb_memcpy2d_async(
-                    ctypes.c_void_p(self.xd.data_ptr() + lo * 4), pitch,
-                    ctypes.c_void_p(x_host.data_ptr() + lo * 4), pitch, (hi - lo) * 4, self.n_src, 1,
-                    ctypes.c_void_p(self.s_in.cuda_stream)))
+                _copy2d(self.xd.data_ptr() + lo * 4, pitch, x_host.data_ptr() + lo * 4, pitch,
+                        (hi - lo) * 4, self.n_src, 1, self.s_in.cuda_stream)
                 e = torch.cuda.Event()
                 e.record(self.s_in)
                 ev_in.append(e)
@@ -201,10 +215,8 @@ class HostAggregator(object):
                 e = torch.cuda.Event()
                 e.record(main)
                 self.s_out.wait_event(e)
-                check(lib.pglb_memcpy2d_async(
-                    ctypes.c_void_p(out_host.data_ptr() + lo * 4), pitch,
-                    ctypes.c_void_p(self.od.data_ptr() + lo * 4), pitch, (hi - lo) * 4, self.n_dst, 2,
-                    ctypes.c_void_p(self.s_out.cuda_stream)))
+                _copy2d(out_host.data_ptr() + lo * 4, pitch, self.od.data_ptr() + lo * 4, pitch,
+                        (hi - lo) * 4, self.n_dst, 2, self.s_out.cuda_stream)
         main.wait_stream(self.s_out)
         return out_host
 
