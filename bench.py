@@ -455,6 +455,7 @@ def main_ours(args):
                    "packed_cols": packed is not None, "l2_hints": bool(packed and packed[1])},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
                      "frac": achieved / hbm_gbs, "traffic": traffic, "peak_source": peak_src,
+                     "frac_of_nominal_8000GBs": achieved / 8000.0,  # SURVEY 8d quotes both denominators
                      "algorithmic_bytes": b_alg, "kernel": "spmm_stream128_kernel<RK=0,SCALED=1,PK=2,YM=0,CFG=1> (+ task_plan, empty_rows, fix-up kernels)",
                      "kernel_ms_mean": kern_ms, "kernel_ms_p10": per[len(per) // 10],
                      "kernel_ms_p90": per[(len(per) * 9) // 10]},
