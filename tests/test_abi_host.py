@@ -168,3 +168,22 @@ def test_argument_validation_of_the_newer_entries():
     assert lib.pglb_reindex_table_init(None, 10, None) < 0
     assert lib.pglb_reindex_graph(one, 3, one, one, 5, one, one, one, one, one, one, 8, None) < 0
     assert b"workspace" in lib.pglb_last_error()
+
+
+def test_plain_c_consumer(tmp_path):
+    """include/pglb.h + libpglb.so from plain C (gcc, no Python in the loop): the binding a maintainer of
+    the reference would write links the same way."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    from pgl_b200 import _lib
+    libdir = os.path.dirname(_lib.LIB_PATH) if hasattr(_lib, "LIB_PATH") else os.path.join(ROOT, "pgl_b200")
+    exe = str(tmp_path / "c_abi_smoke")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c_abi_smoke.c"), "-o", exe, "-L", libdir, "-lpglb",
+           "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0 and "C_ABI_OK indegree=[1 2 1 0 1]" in r.stdout, (r.returncode, r.stdout)
