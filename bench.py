@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- edges/sec per GCN layer (128-d feat) on synthetic power-law graphs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg5|cfg3|cfg4]
 
 One "step" = one GCN-layer aggregation over the whole graph: ``send_recv(sum)`` with both
 degree-norm scalings (reference pgl/nn/conv.py:242-250 around graph.py:860), i.e. the SpMM the
@@ -9,11 +9,21 @@ BASELINE.md roofline table is written for.  Workload (BASELINE.json configs[4], 
 10M nodes / 100M edges Chung-Lu power-law graph (exponent 0.8, ids randomly permuted,
 duplicates and self loops kept), 128-d float32 features.
 
+N > 1 (torchrun, one rank per GPU): the default layout shards the FEATURE COLUMNS (every rank holds the
+whole CSR and 128/N columns of every row: a copy-message aggregation is independent per column, so the
+step needs no exchange at all -- the reference's own large-feature example shards columns the same way,
+examples/.../dist_feat.py:31-49); ``--shard rows`` keeps the 1-D row partition (METIS or block) + halo
+exchange of round 1.
+
 Prints ONE JSON line (rank 0).  Keys follow the driver contract; additionally
   roofline      dominant kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json)
   cpu_baseline  the oracle's C restatement of the reference CPU loop on a bounded sample
+  parity        the GPU result checked against that oracle output on the same inputs, in this run
   e2e           same metric through the public API with pinned HOST buffers (H2D + D2H inside)
-  full_layer    GCNConv(128,128).forward (aggregation + 3xTF32 GEMM + bias + ReLU) edges/s
+  full_layer    GCNConv(128,128).forward (aggregation + dense transform + bias + ReLU) edges/s
+
+``--config cfg3`` (GATConv on RMAT 1M/10M) and ``--config cfg4`` (3-layer GraphSAGE on a products-shape
+graph) time BASELINE.json configs[2] and configs[3] with their own roofline models.
 """
 import argparse
 import ctypes
@@ -29,6 +39,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+PARITY_TOL = 1e-4           # north_star: "correctness matching reference PGL within 1e-4 relative"
 
 
 def parse():
@@ -37,6 +48,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg5", choices=["cfg5", "cfg3", "cfg4"])
     ap.add_argument("--nodes", type=int, default=10_000_000)
     ap.add_argument("--edges", type=int, default=100_000_000)
     ap.add_argument("--dim", type=int, default=128)
@@ -44,6 +56,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=20240922)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-full-layer", action="store_true")
+    ap.add_argument("--shard", default=os.environ.get("PGLB_SHARD", "cols"), choices=["cols", "rows"])
     ap.add_argument("--partition", default="block", choices=["block", "metis"])
     ap.add_argument("--halo", default=os.environ.get("PGLB_HALO_MODE", "p2p"), choices=["nccl", "p2p"])
     ap.add_argument("--overlap", action="store_true")
@@ -112,6 +126,27 @@ def gen_edges(torch, n, e, exponent, seed, device):
     return out
 
 
+def gen_features(torch, n, d, seed, device):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    return torch.randn(n, d, device=device, generator=g)
+
+
+def rmat_edges(torch, scale, e, a=0.57, b=0.19, c=0.19, seed=1, device="cuda"):
+    """RMAT (a, b, c, d) = (0.57, 0.19, 0.19, 0.05), noise off, duplicates / self loops kept."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    src = torch.zeros(e, dtype=torch.int64, device=device)
+    dst = torch.zeros(e, dtype=torch.int64, device=device)
+    for _ in range(scale):
+        r = torch.rand(e, generator=g, device=device)
+        sb = (r >= a + b).to(torch.int64)
+        db = (((r >= a) & (r < a + b)) | (r >= a + b + c)).to(torch.int64)
+        src = src * 2 + sb
+        dst = dst * 2 + db
+    return torch.stack([src, dst], 1)
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons while the timed region runs (NVML)."""
 
@@ -164,14 +199,8 @@ def _ptr(a):
     return ctypes.c_void_p(a.ctypes.data)
 
 
-def cpu_sample_problem(edges_np, n, frac_rows):
-    """Sub-problem of the same workload: all edges whose dst < n_s (ids are randomly permuted so
-    this is a uniform 1/frac sample of rows with their complete in-edge lists); x stays full."""
-    n_s = max(1, int(n * frac_rows))
-    m = edges_np[:, 1] < n_s
-    src = np.ascontiguousarray(edges_np[m, 0])
-    dst = np.ascontiguousarray(edges_np[m, 1])
-    return n_s, src, dst
+def _i64(v):
+    return ctypes.c_int64(int(v))
 
 
 def _load_oracle_c():
@@ -179,98 +208,149 @@ def _load_oracle_c():
     return ctypes.CDLL(obuild.build_oracle_c())
 
 
-def make_cpu_problem(edges_np, n, frac, need_csr):
-    e_total = edges_np.shape[0]
-    n_s, src, dst = cpu_sample_problem(edges_np, n, frac)
-    prob = {"n_s": n_s, "src": src, "dst": dst, "frac": frac,
-            "sample": ("rows dst < %d (%.2f%% of the graph's rows with all their in-edges: %d of "
-                       "%d edges), full %d-row feature matrix" %
-                       (n_s, 100.0 * n_s / n, len(src), e_total, n))}
-    if need_csr:
-        from oracle import oracle as O
-        deg, sv, su, se, ip = O.build_index(dst, src, n_s)
-        prob["ip"], prob["sv"] = ip, sv
-    return prob
+class CpuGcn(object):
+    """The oracle's restatement of the reference CPU path for ONE GCN-layer aggregation
+    (pgl/nn/conv.py:242-250): ``feature * norm`` -> send_u_recv(sum) -> ``output * norm``, on the rows
+    dst < n_s of the workload with ALL their in-edges (ids are randomly permuted, so this is a uniform
+    row sample; frac = 1 is the whole graph) and the full feature matrix.
 
+    ``run(threads)``: threads == 1 -> the sequential COO loop (Paddle's CPU send_u_recv contract);
+    threads > 1 -> the row-threaded CSR twin (bit-identical results, oracle/oracle_c.c)."""
 
-def time_cpu_problem(lib, x_np, prob, dim, threads):
-    """One pass of the oracle's C restatement of the reference CPU loop over `prob`."""
-    n_s, src, dst = prob["n_s"], prob["src"], prob["dst"]
-    out = np.empty((n_s, dim), np.float32)
-    res = {}
-    t0 = time.perf_counter()
-    lib.orc_send_u_recv_f32(_ptr(x_np), _ptr(src), _ptr(dst), ctypes.c_int64(len(src)),
-                            ctypes.c_int64(n_s), ctypes.c_int64(dim), 0, _ptr(out))
-    t1 = time.perf_counter() - t0
-    res["coo_1thread"] = {"edges_per_s": len(src) / t1, "seconds": t1,
-                          "sample_edges": int(len(src)), "sample_rows": int(n_s)}
-    if threads > 1 and "ip" in prob:
-        out2 = np.empty((n_s, dim), np.float32)
+    def __init__(self, lib, src_np, dst_np, n, dim, frac, threads):
+        self.lib, self.n, self.dim, self.frac = lib, int(n), int(dim), float(frac)
+        self.e_total = int(len(src_np))
+        if frac >= 1.0:
+            self.n_s, self.src, self.dst = self.n, src_np, dst_np
+        else:
+            self.n_s = max(1, int(n * frac))
+            m = dst_np < self.n_s
+            self.src = np.ascontiguousarray(src_np[m])
+            self.dst = np.ascontiguousarray(dst_np[m])
+        self.e_s = int(len(self.src))
+        self.ip = self.sv = None
+        if threads > 1:
+            # dst-keyed CSR of the sample (graph preparation, like the GPU's cached index: not timed)
+            deg = np.empty(self.n_s, np.int64)
+            self.ip = np.empty(self.n_s + 1, np.int64)
+            self.sv = np.empty(self.e_s, np.int64)
+            su = np.empty(self.e_s, np.int64)
+            se = np.empty(self.e_s, np.int64)
+            rc = lib.orc_build_index(_ptr(self.dst), _ptr(self.src), _i64(self.e_s), _i64(self.n_s),
+                                     _ptr(deg), _ptr(self.sv), _ptr(su), _ptr(se), _ptr(self.ip))
+            assert rc == 0
+            del su, se, deg
+        self.sample = ("rows dst < %d (%.2f%% of the graph's rows with all their in-edges: %d of %d edges), "
+                       "full %d-row feature matrix" % (self.n_s, 100.0 * self.n_s / self.n, self.e_s,
+                                                       self.e_total, self.n))
+        self.xs = None
+        self.out = None
+
+    def run(self, x_np, norm_np, threads, scaled=True):
+        """One pass.  Returns (seconds charged, detail).  The source scaling touches all N rows whatever
+        the sample is; its time is charged in proportion to the sample (frac), everything else in full."""
+        lib, d = self.lib, self.dim
+        if self.out is None:
+            self.out = np.empty((self.n_s, d), np.float32)
+        t_scale_in = 0.0
+        xin = x_np
+        if scaled:
+            if self.xs is None:
+                self.xs = np.empty_like(x_np)
+            t0 = time.perf_counter()
+            lib.orc_scale_rows_f32(_ptr(x_np), _ptr(norm_np), _i64(self.n), _i64(d), _ptr(self.xs), int(threads))
+            t_scale_in = time.perf_counter() - t0
+            xin = self.xs
         t0 = time.perf_counter()
-        lib.orc_send_u_recv_csr_f32(_ptr(x_np), _ptr(prob["ip"]), _ptr(prob["sv"]),
-                                    ctypes.c_int64(n_s), ctypes.c_int64(dim), 0, _ptr(out2), threads)
-        t2 = time.perf_counter() - t0
-        res["csr_threads"] = {"edges_per_s": len(src) / t2, "seconds": t2, "threads": threads,
-                              "identical_to_coo": bool(np.array_equal(out, out2))}
+        if threads > 1:
+            lib.orc_send_u_recv_csr_f32(_ptr(xin), _ptr(self.ip), _ptr(self.sv), _i64(self.n_s), _i64(d), 0,
+                                        _ptr(self.out), int(threads))
+        else:
+            lib.orc_send_u_recv_f32(_ptr(xin), _ptr(self.src), _ptr(self.dst), _i64(self.e_s), _i64(self.n_s),
+                                    _i64(d), 0, _ptr(self.out))
+        t_agg = time.perf_counter() - t0
+        t_scale_out = 0.0
+        if scaled:
+            t0 = time.perf_counter()
+            lib.orc_scale_rows_f32(_ptr(self.out), _ptr(norm_np), _i64(self.n_s), _i64(d), _ptr(self.out),
+                                   int(threads))
+            t_scale_out = time.perf_counter() - t0
+        charged = t_scale_in * min(1.0, self.n_s / self.n) + t_agg + t_scale_out
+        return charged, {"scale_src_s_full_matrix": t_scale_in, "aggregate_s": t_agg, "scale_dst_s": t_scale_out,
+                         "charged_s": charged, "threads": int(threads), "sample_edges": self.e_s,
+                         "sample_rows": self.n_s, "edges_per_s": self.e_s / charged if charged > 0 else None}
+
+
+def parity_stats(got, want, tol=PARITY_TOL):
+    """got / want: float32 [rows, d] numpy.  max_rel_err = max |got - want| / max |want| (the tests' metric);
+    row_rel_err normalises every row by its own largest entry."""
+    got = np.asarray(got)
+    want = np.asarray(want)
+    diff = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    scale = float(np.abs(want).max()) if want.size else 1.0
+    row_scale = np.maximum(np.abs(want).max(axis=1), 1e-30)
+    row_err = diff.max(axis=1) / row_scale
+    exact = int((got.view(np.uint32) == want.view(np.uint32)).all(axis=1).sum())
+    res = {"rows": int(want.shape[0]), "cols": int(want.shape[1]),
+           "max_rel_err": float(diff.max() / max(scale, 1e-30)) if want.size else 0.0,
+           "max_row_rel_err": float(row_err.max()) if want.size else 0.0,
+           "bit_exact_rows": exact, "tol": tol}
+    res["pass"] = bool(res["max_rel_err"] <= tol and np.isfinite(res["max_rel_err"]))
     return res
 
 
-def calibrate_cpu(lib, edges_np, x_np, n, dim, target_s):
-    """Pick the row fraction whose single-thread pass costs about target_s."""
-    frac = 0.005
-    prob = make_cpu_problem(edges_np, n, frac, need_csr=False)
-    t1 = time_cpu_problem(lib, x_np, prob, dim, 1)["coo_1thread"]["seconds"]
-    return min(1.0, max(frac, frac * target_s / max(t1, 1e-3)))
-
-
-def run_cpu_reference(edges_np, x_np, n, dim, threads, target_s=12.0):
-    lib = _load_oracle_c()
-    frac = calibrate_cpu(lib, edges_np, x_np, n, dim, target_s)
-    prob = make_cpu_problem(edges_np, n, frac, need_csr=threads > 1)
-    res = time_cpu_problem(lib, x_np, prob, dim, threads)
-    res["sample"] = prob["sample"]
-    return res
+def cpu_norm(indeg_np):
+    from oracle import oracle as O
+    return np.ascontiguousarray(O.degree_norm(indeg_np).reshape(-1))
 
 
 def main_reference(args):
+    """The reference's own CPU implementation of the path on the box's host cores, same config as the GPU arm:
+    the whole cfg5 graph when one pass fits the budget (it does on a multi-core host: about a second on 16
+    threads), both norm scalings included."""
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = host_threads()
     dev = "cuda" if torch.cuda.is_available() else "cpu"
-    edges = gen_edges(torch, args.nodes, args.edges, args.exponent, args.seed, dev)
-    edges_np = edges.cpu().numpy()
+    n, d = args.nodes, args.dim
+    edges = gen_edges(torch, n, args.edges, args.exponent, args.seed, dev)
+    src_np = np.ascontiguousarray(edges[:, 0].cpu().numpy())
+    dst_np = np.ascontiguousarray(edges[:, 1].cpu().numpy())
     del edges
-    g = torch.Generator()
-    g.manual_seed(args.seed + 1)
-    x_np = torch.randn(args.nodes, args.dim, generator=g).numpy()
+    x_np = gen_features(torch, n, d, args.seed + 1, dev).cpu().numpy()
+    if dev == "cuda":
+        torch.cuda.empty_cache()
+    norm_np = cpu_norm(np.bincount(dst_np, minlength=n)[:n])
     lib = _load_oracle_c()
-    # one "step" = one pass over a bounded sample of the workload, sized once so that the
-    # whole --steps/--warmup run stays within a couple of minutes
-    per = max(0.5, min(10.0, 100.0 / max(1, args.steps + args.warmup)))
-    frac = calibrate_cpu(lib, edges_np, x_np, args.nodes, args.dim, per)
-    prob = make_cpu_problem(edges_np, args.nodes, frac, need_csr=threads > 1)
+    # budget: the whole --steps/--warmup run within a few minutes
+    total_steps = max(1, args.steps + args.warmup)
+    per = max(0.5, min(12.0, 200.0 / total_steps))
+    probe = CpuGcn(lib, src_np, dst_np, n, d, 0.02, threads)
+    t_probe, _ = probe.run(x_np, norm_np, threads)
+    t_probe2, _ = probe.run(x_np, norm_np, threads)
+    full_est = min(t_probe, t_probe2) / 0.02
+    frac = 1.0 if full_est <= per else max(0.02, per / full_est)
+    del probe
+    prob = CpuGcn(lib, src_np, dst_np, n, d, frac, threads)
     vals, info = [], None
     for i in range(args.warmup + args.steps):
-        info = time_cpu_problem(lib, x_np, prob, args.dim, threads)
-        best = max(v["edges_per_s"] for v in info.values())
+        t, info = prob.run(x_np, norm_np, threads)
         if i >= args.warmup:
-            vals.append(best)
+            vals.append(prob.e_s / t)
     v = float(np.median(vals))
-    used = threads if "csr_threads" in info and \
-        info["csr_threads"]["edges_per_s"] >= info["coo_1thread"]["edges_per_s"] else 1
     line = {
         "impl": "reference", "metric": "edges/sec per GCN layer (128-d feat)", "value": v,
         "unit": "edges/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * args.edges / v, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "note": "reference CPU path restated (Paddle "
-                   "unavailable in this image): oracle/oracle_c.c -- the sequential COO loop of "
-                   "paddle.geometric.send_u_recv's CPU contract and its row-threaded CSR twin "
-                   "(bit-identical results); value = the faster of the two"},
-        "cpu_baseline": {"value": v, "unit": "edges/s", "cores": used, "kind": "port",
-                         "sample": prob["sample"], "detail": info},
+        "config": {"workload": workload_name(args), "same_workload_as_gpu_arm": frac >= 1.0,
+                   "note": "reference CPU path restated (Paddle unavailable in this image): oracle/oracle_c.c -- "
+                           "feature*norm, send_u_recv(sum) as the row-threaded CSR twin of Paddle's sequential "
+                           "COO loop (bit-identical results), output*norm; all host threads"},
+        "cpu_baseline": {"value": v, "unit": "edges/s", "cores": threads, "kind": "port",
+                         "sample": prob.sample, "detail": info},
         "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -285,6 +365,49 @@ def workload_name(args):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
+
+def _ev(torch):
+    return torch.cuda.Event(enable_timing=True)
+
+
+def timed_steps(torch, step, steps, dist=None):
+    """EXACTLY `steps` calls bracketed by synchronize (+ barrier) on both sides; per-step CUDA events on the
+    launching stream.  Returns (total_ms, sorted per-step ms)."""
+    evs = [(_ev(torch), _ev(torch)) for _ in range(steps)]
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    b0, b1 = _ev(torch), _ev(torch)
+    b0.record()
+    for a, b in evs:
+        a.record()
+        step()
+        b.record()
+    b1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    return b0.elapsed_time(b1), sorted(a.elapsed_time(b) for a, b in evs)
+
+
+def read_traffic(key):
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            return json.load(open(tp)).get(key)
+        except Exception:
+            return None
+    return None
+
+
+def kernel_name():
+    v5 = os.environ.get("PGLB_STREAM_V5")
+    try:
+        from pgl_b200 import ops
+        return ops.stream_kernel_name()
+    except Exception:
+        return "spmm_stream (PGLB_STREAM_V5=%s)" % v5
+
 
 def main_ours(args):
     import torch
@@ -304,176 +427,345 @@ def main_ours(args):
     from pgl_b200 import ops
     import pgl_b200.nn.functional as GF
 
+    if args.config == "cfg3":
+        result = bench_gat(args, torch, pgl, ops, GF, dev) if rank == 0 else None
+    elif args.config == "cfg4":
+        result = bench_sage(args, torch, dist, pgl, ops, GF, dev, world, rank)
+    elif world > 1 and args.shard == "rows":
+        result = bench_row_sharded(args, torch, dist, pgl, dev, world, rank)
+    else:
+        result = bench_gcn(args, torch, dist if world > 1 else None, pgl, ops, GF, dev, world, rank)
+    if rank == 0 and result is not None:
+        print(json.dumps(result))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if result is not None and result.get("parity") and result["parity"].get("pass") is False:
+        raise SystemExit("bench.py: parity check against the oracle FAILED: %r" % (result["parity"],))
+
+
+def bench_gcn(args, torch, dist, pgl, ops, GF, dev, world, rank):
+    """cfg5 at 1 GPU, and column-sharded at N GPUs (rank r owns columns [r*D/N, (r+1)*D/N) of every row)."""
     n, e, d = args.nodes, args.edges, args.dim
+    assert d % world == 0 and (d // world) % 4 == 0, "feature width must split into 16-byte column slices"
+    dl = d // world
+    c0 = rank * dl
     hbm_gbs, peak_src = peaks()
 
     t0 = time.perf_counter()
-    edges = gen_edges(torch, n, e, args.exponent, args.seed, dev)
+    edges = gen_edges(torch, n, e, args.exponent, args.seed, dev)   # same seed: every rank holds the whole graph
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t0
-
-    if world > 1:
-        from pgl_b200.distributed import ShardedGraph
-        sg = ShardedGraph.from_global_edges(edges, n, world, rank, method=args.partition,
-                                            mode=args.halo, overlap=args.overlap)
-        del edges
-        torch.cuda.empty_cache()
-        result = bench_sharded(args, torch, dist, pgl, sg, dev, world, rank, hbm_gbs, peak_src)
-        if rank == 0:
-            print(json.dumps(result))
-        dist.barrier()
-        dist.destroy_process_group()
-        return
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     g = pgl.Graph(edges=edges, num_nodes=n)
-    s0, s1 = ev(), ev()
+    s0, s1 = _ev(torch), _ev(torch)
+    g._fwd_csr()                     # first call pays one-off costs (module load, workspace growth): not the build time
+    g2 = pgl.Graph(edges=edges, num_nodes=n)
+    torch.cuda.synchronize()
     s0.record()
-    fwd = g._fwd_csr()  # device CSR build (one-off, cached on the graph)
+    g2._fwd_csr()                    # device CSR build, steady state
     s1.record()
     torch.cuda.synchronize()
     t_csr_ms = s0.elapsed_time(s1)
+    del g2
+    fwd = g._fwd_csr()
     norm = GF.degree_norm(g).reshape(-1)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(args.seed + 1)
-    x = torch.randn(n, d, device=dev, generator=gen)
-    out = torch.empty(n, d, device=dev)
-
-    packed = fwd["packed"](n, d * 4)  # cached packed column ids, built once per graph
+    x_full = gen_features(torch, n, d, args.seed + 1, dev)
+    x = x_full if world == 1 else x_full[:, c0:c0 + dl].contiguous()
+    del x_full
+    torch.cuda.empty_cache()
+    out = torch.empty(n, dl, device=dev)
+    packed = fwd["packed"](n, dl * 4)  # cached packed column ids, built once per graph
 
     def step():
         return ops._spmm_raw(fwd["indptr"], fwd["cols"], x, n, "sum", scale_src=norm,
                              scale_dst=norm, max_degree=fwd["max_degree"], out=out, packed=packed)
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev.index)
     sampler.start()
     l0 = ops.launch_count()
-    evs = [(ev(), ev()) for _ in range(args.steps)]
-    torch.cuda.synchronize()
-    b0, b1 = ev(), ev()
-    b0.record()
-    for a, b in evs:
-        a.record()
-        step()
-        b.record()
-    b1.record()
-    torch.cuda.synchronize()
+    total_ms, per = timed_steps(torch, step, args.steps, dist)
     launches = ops.launch_count() - l0
     clocks = sampler.stop()
-    total_ms = b0.elapsed_time(b1)
-    per = sorted(a.elapsed_time(b) for a, b in evs)
+    kern_ms = float(np.mean(per))
+    if dist is not None:
+        t = torch.tensor([total_ms, kern_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, kern_ms = float(t[0].item()), float(t[1].item())
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
     ms_step = total_ms / args.steps
     value = e / (ms_step * 1e-3)
-    b_alg = algorithmic_bytes(n, e, d)
-    kern_ms = float(np.mean(per))
+    b_alg = algorithmic_bytes(n, e, dl)            # per GPU: every edge, D/N columns
     achieved = b_alg / (kern_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("spmm_csr_kernel_bytes_per_launch")
-        except Exception:
-            traffic = None
 
-    # full GCN layer through the public API (aggregation + fp32 GEMM + bias + ReLU)
-    conv = pgl.nn.GCNConv(d, d, activation="relu").to(dev)
-    with torch.no_grad():
-        for _ in range(3):
-            y = conv(g, x)
-        torch.cuda.synchronize()
-        f0, f1 = ev(), ev()
-        f0.record()
-        kf = max(3, args.steps // 4)
-        for _ in range(kf):
-            y = conv(g, x)
-        f1.record()
-        torch.cuda.synchronize()
-        full_ms = f0.elapsed_time(f1) / kf
-    del y
-
-    # e2e: public API, pinned host buffers, H2D of the step's input + D2H of its result inside
-    e2e = None
-    x_host = None
-    if not args.no_e2e:
-        try:
-            x_host = torch.empty((n, d), dtype=torch.float32, pin_memory=True)
-            x_host.copy_(x)
-            out_host = torch.empty((n, d), dtype=torch.float32, pin_memory=True)
-            chunks = int(os.environ.get("PGLB_E2E_CHUNKS", "2"))
-
-            def e2e_step():
-                # public host-buffer API: upload / aggregate / download pipelined by column chunks
-                g.send_recv_host(x_host, out_host, "sum", scale_src=norm, scale_dst=norm, chunks=chunks)
-
-            for _ in range(2):
-                e2e_step()
-            torch.cuda.synchronize()
-            ke = max(3, min(args.steps, 8))
-            q0, q1 = ev(), ev()
-            q0.record()
-            for _ in range(ke):
-                e2e_step()
-            q1.record()
-            torch.cuda.synchronize()
-            e2e_ms = q0.elapsed_time(q1) / ke
-            e2e = {"value": e / (e2e_ms * 1e-3), "unit": "edges/s",
-                   "h2d_bytes_per_step": n * d * 4, "d2h_bytes_per_step": n * d * 4,
-                   "ms_per_step": e2e_ms, "steps": ke,
-                   "api": "Graph.send_recv_host(sum)+degree norms on a resident graph; features from "
-                          "pinned host memory, result back in pinned host memory; %d column "
-                          "chunks pipelined over H2D / kernel / D2H streams" % chunks}
-            # the pipelined path must agree with the resident path
-            ref = g._send_u_recv(x, "sum", None, scale_src=norm, scale_dst=norm)
-            e2e["max_abs_diff_vs_resident"] = float((out_host.to(dev) - ref).abs().max().item())
-            del ref
-        except Exception as ex:
-            e2e = {"value": None, "unit": "edges/s", "error": repr(ex)[:200]}
-
+    # ---- parity against the oracle, in this run ---------------------------------------------
     cpu = None
+    parity = None
     if not args.no_cpu:
         try:
-            edges_np = edges.cpu().numpy()
-            x_np = x_host.numpy() if x_host is not None else x.cpu().numpy()
-            info = run_cpu_reference(edges_np, x_np, n, d, threads=host_threads(), target_s=12.0)
-            cpu = {"value": info["coo_1thread"]["edges_per_s"], "unit": "edges/s", "cores": 1,
-                   "kind": "port", "sample": info["sample"], "detail": info}
+            cpu, parity = cpu_and_parity(args, torch, dist, ops, fwd, edges, x, norm, out, step, dev, world, rank,
+                                         n, d, dl)
         except Exception as ex:
-            cpu = {"value": None, "unit": "edges/s", "cores": 1, "kind": "port",
-                   "sample": "failed: %r" % (ex,)}
+            cpu = {"value": None, "unit": "edges/s", "cores": 1, "kind": "port", "sample": "failed: %r" % (ex,)}
+            parity = {"pass": None, "error": repr(ex)[:300]}
 
-    result = {
+    # ---- full GCN layer through the public API -----------------------------------------------
+    full = None
+    if not args.no_full_layer:
+        try:
+            full = full_layer(args, torch, dist, pgl, g, x, norm, dev, world, rank, n, e, d, dl)
+        except Exception as ex:
+            full = {"value": None, "error": repr(ex)[:300]}
+
+    # ---- e2e: public API, pinned host buffers, H2D of the step's input + D2H of its result inside
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = e2e_host(args, torch, dist, g, x, norm, dev, world, n, e, dl)
+        except Exception as ex:
+            e2e = {"value": None, "unit": "edges/s", "error": repr(ex)[:300]}
+
+    par = "single GPU" if world == 1 else \
+        ("%d-way COLUMN shard: every GPU holds the whole CSR and %d of the %d feature columns of all rows; the "
+         "aggregation needs no exchange (full_layer adds the [N, D/R] -> [N/R, D] all-to-all)" % (world, dl, d))
+    return {
         "metric": "edges/sec per GCN layer (128-d feat)", "value": value, "unit": "edges/s",
-        "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(args), "l2": "inputs (5.1 GB features) larger than L2",
-                   "parallelism": "single GPU", "csr_build_ms": t_csr_ms, "graph_gen_s": t_gen,
+        "config": {"workload": workload_name(args),
+                   "l2": "inputs (%.2f GB of feature rows per GPU) larger than L2" % (n * dl * 4 / 1e9),
+                   "parallelism": par, "csr_build_ms": t_csr_ms, "graph_gen_s": t_gen,
                    "max_in_degree": int(fwd["max_degree"]), "index_dtype": "int64",
-                   "packed_cols": packed is not None, "l2_hints": bool(packed and packed[1])},
+                   "packed_cols": packed is not None, "l2_hints": bool(packed and packed[1]),
+                   "stream_v5": os.environ.get("PGLB_STREAM_V5", "default")},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
-                     "frac": achieved / hbm_gbs, "traffic": traffic, "peak_source": peak_src,
-                     "frac_of_nominal_8000GBs": achieved / 8000.0,  # SURVEY 8d quotes both denominators
-                     "algorithmic_bytes": b_alg, "kernel": "spmm_stream128_kernel<RK=0,SCALED=1,PK=2,YM=0,CFG=1> (+ task_plan, empty_rows, fix-up kernels)",
-                     "kernel_ms_mean": kern_ms, "kernel_ms_p10": per[len(per) // 10],
-                     "kernel_ms_p90": per[(len(per) * 9) // 10]},
-        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "full_layer": {"value": e / (full_ms * 1e-3), "unit": "edges/s", "ms": full_ms,
-                       "what": "GCNConv(128,128,relu).forward: aggregation + 3xTF32 tensor-core GEMM "
-                               "with bias + ReLU in its epilogue (PGLB_TC_GEMM=0: fp32 addmm + ReLU)"},
+                     "frac": achieved / hbm_gbs,
+                     "traffic": read_traffic("spmm_csr_kernel_bytes_per_launch" if world == 1 else
+                                             "colshard%d_bytes_per_launch" % world),
+                     "peak_source": peak_src, "frac_of_nominal_8000GBs": achieved / 8000.0,
+                     "algorithmic_bytes": b_alg,
+                     "note": "per GPU: E*(4*Dl+8) + N*4*Dl + (N+1)*8 + 2*N*4 with Dl = %d columns, over the slowest "
+                             "rank's mean kernel time (CUDA events around each step on the launching stream)" % dl,
+                     "kernel": kernel_name(), "kernel_ms_mean": kern_ms,
+                     "kernel_ms_p10": per[len(per) // 10], "kernel_ms_p90": per[(len(per) * 9) // 10]},
+        "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "full_layer": full,
     }
-    print(json.dumps(result))
 
 
-def bench_sharded(args, torch, dist, pgl, sg, dev, world, rank, hbm_gbs, peak_src):
+def cpu_and_parity(args, torch, dist, ops, fwd, edges, x, norm, out, step, dev, world, rank, n, d, dl):
+    """Rank 0: the oracle's 1-thread COO pass on a bounded row sample (cpu_baseline).  Every rank: its
+    columns of the GPU output on the sample rows against the oracle's output for the same inputs --
+    (a) the GCN-normalised aggregation (tolerance 1e-4: the kernel fuses x*norm into an FMA),
+    (b) the plain sum, which must be BIT-EXACT on every row of <= 1024 in-edges (same summation order)."""
+    lib = _load_oracle_c()
+    src_np = np.ascontiguousarray(edges[:, 0].cpu().numpy())
+    dst_np = np.ascontiguousarray(edges[:, 1].cpu().numpy())
+    x_np = x.cpu().numpy()
+    norm_np = norm.cpu().numpy()
+    indeg = fwd["degree"].cpu().numpy()
+    norm_ref = cpu_norm(indeg)
+    threads = host_threads()
+    cpu = None
+    if rank == 0:
+        # calibrate: about 12 s of single-thread work
+        probe = CpuGcn(lib, src_np, dst_np, n, dl, 0.005, 1)
+        t1, _ = probe.run(x_np, norm_ref, 1)
+        frac = min(1.0, max(0.005, 0.005 * 12.0 / max(t1, 1e-3)))
+        del probe
+    else:
+        frac = 0.0
+    if dist is not None:
+        ft = torch.tensor([frac], device=dev, dtype=torch.float64)
+        dist.broadcast(ft, 0)
+        frac = float(ft.item())
+    if rank != 0:
+        frac = min(frac, 0.02)  # the other ranks only check: a 2 % row sample of their columns
+    prob = CpuGcn(lib, src_np, dst_np, n, dl, frac, threads)
+    n_s = prob.n_s
+    if rank == 0:
+        t1, det1 = prob.run(x_np, norm_ref, 1)
+        cpu = {"value": prob.e_s / t1, "unit": "edges/s", "cores": 1, "kind": "port", "sample": prob.sample,
+               "detail": {"coo_1thread": det1}}
+        want = prob.out.copy()
+        if threads > 1:
+            tt, dett = prob.run(x_np, norm_ref, threads)
+            cpu["detail"]["csr_threads"] = dict(dett, identical_to_coo=bool(np.array_equal(want, prob.out)))
+    else:
+        prob.run(x_np, norm_ref, threads)
+        want = prob.out.copy()
+    step()
+    torch.cuda.synchronize()
+    got = out[:n_s].cpu().numpy()
+    parity = parity_stats(got, want)
+    parity["norm_bit_exact"] = bool(np.array_equal(norm_np, norm_ref))
+    # (b) plain sum, bit-exact where the order is the sequential one
+    prob.run(x_np, norm_ref, threads, scaled=False)
+    plain = ops._spmm_raw(fwd["indptr"], fwd["cols"], x, n, "sum", max_degree=fwd["max_degree"],
+                          packed=fwd["packed"](n, dl * 4))
+    torch.cuda.synchronize()
+    gp = plain[:n_s].cpu().numpy()
+    del plain
+    short = indeg[:n_s] <= 1024
+    ex_rows = (gp.view(np.uint32) == prob.out.view(np.uint32)).all(axis=1)
+    ps = parity_stats(gp, prob.out)
+    parity["plain_sum"] = {"max_rel_err": ps["max_rel_err"], "bit_exact_rows": int(ex_rows.sum()),
+                           "rows_le_1024_edges": int(short.sum()),
+                           "all_rows_le_1024_bit_exact": bool(ex_rows[short].all()),
+                           "rows_gt_1024_edges": int((~short).sum())}
+    parity["pass"] = bool(parity["pass"] and ps["pass"] and parity["plain_sum"]["all_rows_le_1024_bit_exact"])
+    parity["what"] = ("rank %d: GPU output rows dst < %d, columns [%d, %d) vs oracle/oracle_c.c on the same edges and "
+                      "features" % (rank, n_s, rank * dl, rank * dl + dl))
+    if dist is not None:
+        allp = [None] * world
+        dist.all_gather_object(allp, parity)
+        parity = {"pass": all(bool(p["pass"]) for p in allp), "tol": PARITY_TOL,
+                  "max_rel_err": max(p["max_rel_err"] for p in allp),
+                  "rows": sum(p["rows"] for p in allp),
+                  "bit_exact_rows": sum(p["plain_sum"]["bit_exact_rows"] for p in allp), "per_rank": allp}
+    else:
+        parity["bit_exact_rows_gcn"] = parity["bit_exact_rows"]
+        parity["bit_exact_rows"] = parity["plain_sum"]["bit_exact_rows"]
+    return cpu, parity
+
+
+def full_layer(args, torch, dist, pgl, g, x, norm, dev, world, rank, n, e, d, dl):
+    """GCNConv(128,128,relu).forward.  N = 1: the public layer.  N > 1: aggregate my columns (no exchange) ->
+    all-to-all [N, D/R] -> [N/R, D] -> dense transform + bias + ReLU of my row block."""
+    kf = max(3, args.steps // 4)
+    if world == 1:
+        conv = pgl.nn.GCNConv(d, d, activation="relu").to(dev)
+        with torch.no_grad():
+            for _ in range(3):
+                y = conv(g, x)
+            torch.cuda.synchronize()
+            f0, f1 = _ev(torch), _ev(torch)
+            f0.record()
+            for _ in range(kf):
+                y = conv(g, x)
+            f1.record()
+            torch.cuda.synchronize()
+            full_ms = f0.elapsed_time(f1) / kf
+        del y
+        return {"value": e / (full_ms * 1e-3), "unit": "edges/s", "ms": full_ms,
+                "what": "GCNConv(128,128,relu).forward: aggregation + dense transform with bias + ReLU in its "
+                        "epilogue (3xTF32 tensor cores, csrc/linear_tc.cu)"}
+    from pgl_b200.distributed import ColumnShardedGraph
+    from pgl_b200 import ops
+    cs = ColumnShardedGraph(g, d, world, rank)
+    torch.manual_seed(7)
+    w = (torch.randn(d, d, device=dev) / d ** 0.5).contiguous()
+    b = torch.zeros(d, device=dev)
+
+    def layer():
+        agg = cs.gcn_aggregate(x, norm)
+        rows = cs.to_rows(agg)
+        return ops.linear_tc(rows, w, b, "relu")
+
+    with torch.no_grad():
+        for _ in range(3):
+            layer()
+        torch.cuda.synchronize()
+        dist.barrier()
+        f0, f1 = _ev(torch), _ev(torch)
+        f0.record()
+        for _ in range(kf):
+            layer()
+        f1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([f0.elapsed_time(f1) / kf], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        full_ms = float(t.item())
+    return {"value": e / (full_ms * 1e-3), "unit": "edges/s", "ms": full_ms,
+            "what": "column-sharded GCN layer: aggregate my %d columns (no exchange) -> NCCL all-to-all to whole rows "
+                    "of my row block -> dense transform + bias + ReLU; output row-sharded [N/%d, %d]" % (dl, world, d)}
+
+
+def e2e_host(args, torch, dist, g, x, norm, dev, world, n, e, dl):
+    """Public host-buffer API: this rank's [N, Dl] feature columns start in pinned host memory and its result ends
+    in pinned host memory, every step.  `value` pipelines successive steps (HostAggregator.submit / wait: the
+    upload of step i+1 overlaps the kernel and download of step i over full-duplex PCIe); `single_call_ms` is one
+    blocking Graph.send_recv_host call."""
+    x_host = torch.empty((n, dl), dtype=torch.float32, pin_memory=True)
+    x_host.copy_(x)
+    out_host = torch.empty((n, dl), dtype=torch.float32, pin_memory=True)
+    chunks = int(os.environ.get("PGLB_E2E_CHUNKS", "2"))
+    for _ in range(2):
+        g.send_recv_host(x_host, out_host, "sum", scale_src=norm, scale_dst=norm, chunks=chunks)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    g.send_recv_host(x_host, out_host, "sum", scale_src=norm, scale_dst=norm, chunks=chunks)
+    single_ms = (time.perf_counter() - t0) * 1e3
+    ref = g._send_u_recv(x, "sum", None, scale_src=norm, scale_dst=norm)
+    diff_single = float((out_host.to(dev) - ref).abs().max().item())
+
+    agg = g.host_aggregator(n, dl, chunks=int(os.environ.get("PGLB_E2E_PIPE_CHUNKS", "1")), depth=2)
+    out_host.zero_()
+    for _ in range(2):
+        agg.wait(agg.submit(x_host, out_host, "sum", scale_src=norm, scale_dst=norm))
+    ke = max(3, min(args.steps, 8))
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    q0, q1 = _ev(torch), _ev(torch)
+    q0.record()
+    tickets = [agg.submit(x_host, out_host, "sum", scale_src=norm, scale_dst=norm) for _ in range(ke)]
+    for t in tickets:
+        torch.cuda.current_stream().wait_event(t)
+    q1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e2e_ms = q0.elapsed_time(q1) / ke
+    diff_pipe = float((out_host.to(dev) - ref).abs().max().item())
+    del ref
+    nbytes = n * dl * 4
+    if dist is not None:
+        t = torch.tensor([e2e_ms, single_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms, single_ms = float(t[0].item()), float(t[1].item())
+        nbytes *= world
+    return {"value": e / (e2e_ms * 1e-3), "unit": "edges/s",
+            "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+            "ms_per_step": e2e_ms, "steps": ke, "single_call_ms": single_ms,
+            "max_abs_diff_vs_resident": max(diff_single, diff_pipe),
+            "api": "Graph.host_aggregator(...).submit/wait (sum + degree norms) on a resident graph: features from "
+                   "pinned host memory, result back in pinned host memory, every step; successive steps are "
+                   "double-buffered so the upload of step i+1 overlaps kernel + download of step i.  "
+                   "single_call_ms = one blocking Graph.send_recv_host call (%d column chunks)" % chunks}
+
+
+# ------------------------------------------------------------------------------------------
+# N > 1, 1-D row partition + halo exchange (round 1's layout; the north_star's METIS variant)
+# ------------------------------------------------------------------------------------------
+
+def bench_row_sharded(args, torch, dist, pgl, dev, world, rank):
+    from pgl_b200.distributed import ShardedGraph
+    from pgl_b200 import ops
     n, e, d = args.nodes, args.edges, args.dim
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(args.seed + 1 + rank)
+    hbm_gbs, peak_src = peaks()
+    edges = gen_edges(torch, n, e, args.exponent, args.seed, dev)
+    sg = ShardedGraph.from_global_edges(edges, n, world, rank, method=args.partition,
+                                        mode=args.halo, overlap=args.overlap)
+    torch.cuda.empty_cache()
     x_ext, x_local = sg.features(d)  # features live inside the exchange buffer: no staging copy
-    x_local.copy_(torch.randn(sg.n_local, d, device=dev, generator=gen))
+    x_full = gen_features(torch, n, d, args.seed + 1, dev)
+    owned = sg.owned_global_ids() if hasattr(sg, "owned_global_ids") else None
+    if owned is not None:
+        x_local.copy_(x_full[owned])
+    else:
+        g0 = torch.Generator(device=dev)
+        g0.manual_seed(args.seed + 1 + rank)
+        x_local.copy_(torch.randn(sg.n_local, d, device=dev, generator=g0))
     norm_l = sg.local_norm()
 
     def step():
@@ -482,22 +774,13 @@ def bench_sharded(args, torch, dist, pgl, sg, dev, world, rank, hbm_gbs, peak_sr
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
-    dist.barrier()
     sampler = ClockSampler(dev.index)
     sampler.start()
-    from pgl_b200 import ops
     l0 = ops.launch_count()
-    torch.cuda.synchronize()
-    b0, b1 = ev(), ev()
-    b0.record()
-    for _ in range(args.steps):
-        step()
-    b1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
+    total_ms, per = timed_steps(torch, step, args.steps, dist)
     launches = ops.launch_count() - l0
     clocks = sampler.stop()
-    ms = torch.tensor([b0.elapsed_time(b1)], device=dev, dtype=torch.float64)
+    ms = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms.item()) / args.steps
     stats = sg.stats()
@@ -507,49 +790,42 @@ def bench_sharded(args, torch, dist, pgl, sg, dev, world, rank, hbm_gbs, peak_sr
     allcomp = [None] * world
     dist.all_gather_object(allcomp, comp)
     value = e / (ms_step * 1e-3)
-    b_alg = max(algorithmic_bytes(s["n_local"], s["e_local"], d) + 2 * s["halo_rows"] * 4 * d
-                for s in allstats)
+    # the timed kernel's own bytes (no exchange term in the aggregation's roofline)
+    b_alg = max(algorithmic_bytes(s["n_local"], s["e_local"], d) for s in allstats)
     agg_ms = max(c["aggregate_ms"] for c in allcomp)
     achieved = b_alg / (agg_ms * 1e-3) / 1e9
 
-    # e2e: every rank keeps its own feature rows in pinned host memory; a step copies them in,
-    # runs the sharded aggregation (halo exchange included) and reads its output rows back
-    e2e = None
-    if not args.no_e2e:
+    parity = None
+    if not args.no_cpu and owned is not None:
         try:
-            xh = torch.empty((sg.n_local, d), dtype=torch.float32, pin_memory=True)
-            xh.copy_(x_local)
-            oh = torch.empty((sg.n_local, d), dtype=torch.float32, pin_memory=True)
-
-            def e2e_step():
-                x_local.copy_(xh, non_blocking=True)
-                o = sg.gcn_aggregate(x_local, norm_l)
-                oh.copy_(o, non_blocking=True)
-
-            for _ in range(2):
-                e2e_step()
-            torch.cuda.synchronize()
-            dist.barrier()
-            ke = max(3, min(args.steps, 8))
-            q0, q1 = ev(), ev()
-            q0.record()
-            for _ in range(ke):
-                e2e_step()
-            q1.record()
-            torch.cuda.synchronize()
-            dist.barrier()
-            t = torch.tensor([q0.elapsed_time(q1)], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item()) / ke
-            nb = torch.tensor([sg.n_local * d * 4], device=dev, dtype=torch.float64)
-            dist.all_reduce(nb)
-            e2e = {"value": e / (e2e_ms * 1e-3), "unit": "edges/s",
-                   "h2d_bytes_per_step": int(nb.item()), "d2h_bytes_per_step": int(nb.item()),
-                   "ms_per_step": e2e_ms, "steps": ke,
-                   "api": "ShardedGraph.gcn_aggregate: per-rank feature rows from pinned host memory, "
-                          "halo exchange + aggregation on the GPUs, output rows back to pinned host memory"}
+            # oracle on a sample of MY rows: global edges whose dst is one of my first rows
+            lib = _load_oracle_c()
+            k = min(int(owned.numel()), 20000)
+            mine = owned[:k]
+            sel = torch.zeros(n, dtype=torch.bool, device=dev)
+            sel[mine] = True
+            m = sel[edges[:, 1]]
+            relabel = torch.full((n,), -1, dtype=torch.int64, device=dev)
+            relabel[mine] = torch.arange(k, device=dev)
+            src_np = np.ascontiguousarray(edges[m, 0].cpu().numpy())
+            dst_np = np.ascontiguousarray(relabel[edges[m, 1]].cpu().numpy())
+            indeg = torch.bincount(edges[:, 1], minlength=n)
+            norm_ref = cpu_norm(indeg.cpu().numpy())
+            xs = np.ascontiguousarray(x_full.cpu().numpy() * norm_ref[:, None])
+            want = np.empty((k, d), np.float32)
+            lib.orc_send_u_recv_f32(_ptr(xs), _ptr(src_np), _ptr(dst_np), _i64(len(src_np)), _i64(k), _i64(d), 0,
+                                    _ptr(want))
+            want *= norm_ref[mine.cpu().numpy()][:, None]
+            got = step()[:k].cpu().numpy()
+            parity = parity_stats(got, want)
+            allp = [None] * world
+            dist.all_gather_object(allp, parity)
+            parity = {"pass": all(p["pass"] for p in allp), "tol": PARITY_TOL,
+                      "max_rel_err": max(p["max_rel_err"] for p in allp), "rows": sum(p["rows"] for p in allp),
+                      "bit_exact_rows": sum(p["bit_exact_rows"] for p in allp), "per_rank": allp}
         except Exception as ex:
-            e2e = {"value": None, "unit": "edges/s", "error": repr(ex)[:200]}
+            parity = {"pass": None, "error": repr(ex)[:300]}
+    del x_full
     return {
         "metric": "edges/sec per GCN layer (128-d feat)", "value": value, "unit": "edges/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
@@ -561,9 +837,252 @@ def bench_sharded(args, torch, dist, pgl, sg, dev, world, rank, hbm_gbs, peak_sr
                    "per_rank": allstats, "time_split_ms": allcomp},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
                      "frac": achieved / hbm_gbs, "traffic": None, "peak_source": peak_src,
-                     "note": "slowest rank's local aggregation kernel; exchange time in time_split_ms"},
-        "cpu_baseline": None, "e2e": e2e,
+                     "note": "slowest rank's local aggregation kernel over its own algorithmic bytes; the "
+                             "exchange is in time_split_ms"},
+        "cpu_baseline": None, "parity": parity, "e2e": None,
         "gpu_launches": int(launches), "clocks": clocks,
+    }
+
+
+# ------------------------------------------------------------------------------------------
+# cfg3: GATConv(128 -> 8 x 16) on RMAT scale 20 / 10M edges (BASELINE.json configs[2])
+# ------------------------------------------------------------------------------------------
+
+def bench_gat(args, torch, pgl, ops, GF, dev):
+    n, e, H, Dh = 1 << 20, 10_000_000, 8, 16
+    hbm_gbs, peak_src = peaks()
+    edges = rmat_edges(torch, 20, e, seed=1, device=dev)
+    g = pgl.Graph(edges=edges, num_nodes=n)
+    x = gen_features(torch, n, 128, 2, dev)
+    torch.manual_seed(3)
+    conv = pgl.nn.GATConv(128, Dh, feat_drop=0, attn_drop=0, num_heads=H).to(dev)
+    conv.eval()
+    csr = g._fwd_csr()
+    with torch.no_grad():
+        f = (x @ conv.linear.weight + conv.linear.bias).reshape(-1, H, Dh).contiguous()
+        a_s = (f * conv.weight_src).sum(-1).contiguous()
+        a_d = (f * conv.weight_dst).sum(-1).contiguous()
+
+        def step():
+            return ops.gat_fused(csr, f, a_s, a_d, 0.2)
+
+        for _ in range(max(args.warmup, 3)):
+            step()
+        sampler = ClockSampler(dev.index)
+        sampler.start()
+        l0 = ops.launch_count()
+        total_ms, per = timed_steps(torch, step, args.steps)
+        launches = ops.launch_count() - l0
+        clocks = sampler.stop()
+        for _ in range(3):
+            conv(g, x)
+        torch.cuda.synchronize()
+        f0, f1 = _ev(torch), _ev(torch)
+        f0.record()
+        for _ in range(5):
+            conv(g, x)
+        f1.record()
+        torch.cuda.synchronize()
+        layer_ms = f0.elapsed_time(f1) / 5
+        # parity at full size: sampled rows against the oracle's op-by-op GAT aggregation
+        parity = None
+        if not args.no_cpu:
+            try:
+                parity = gat_parity(torch, edges, n, f, a_s, a_d, step(), H, Dh)
+            except Exception as ex:
+                parity = {"pass": None, "error": repr(ex)[:300]}
+    ms_step = total_ms / args.steps
+    kern_ms = float(np.mean(per))
+    # per edge 8 + 32 + 512 + 32 (alpha write, training only) ; per node 32 + 512 + 8.
+    # The single-pass inference kernel writes no alpha: 552 B/edge.
+    b_alg = e * (8 + 32 + 512) + n * (32 + 512 + 8)
+    achieved = b_alg / (kern_ms * 1e-3) / 1e9
+    return {
+        "metric": "edges/sec per GAT layer aggregation (8 heads x 16, edge softmax fused)", "value": e / (ms_step * 1e-3),
+        "unit": "edges/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg3 RMAT scale 20 (0.57,0.19,0.19,0.05), %d nodes / %d edges, GATConv(128 -> 8x16) eval: "
+                               "single-pass attention + softmax + aggregation" % (n, e),
+                   "max_in_degree": int(csr["max_degree"]), "l2": "features (0.5 GB) larger than L2"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
+                     "traffic": read_traffic("gat_fused_bytes_per_launch"), "peak_source": peak_src,
+                     "algorithmic_bytes": b_alg, "kernel": "spmm_stream128_kernel<YM=2> (fused GAT)",
+                     "kernel_ms_mean": kern_ms,
+                     "note": "SURVEY 8d cfg3 model without the alpha write (inference): E*552 + N*552 bytes; with the "
+                             "training-time alpha write the model is 6.42 GB"},
+        "parity": parity, "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+        "full_layer": {"ms": layer_ms, "value": e / (layer_ms * 1e-3), "unit": "edges/s",
+                       "what": "GATConv.forward (linear + attention logits + fused aggregation)"},
+    }
+
+
+def gat_parity(torch, edges, n, f, a_s, a_d, got, H, Dh, rows=4096):
+    """Oracle (numpy, op by op as pgl/nn/conv.py:308-346) on a row sample at full size."""
+    dev = f.device
+    g0 = torch.Generator(device=dev)
+    g0.manual_seed(11)
+    pick = torch.randperm(n, generator=g0, device=dev)[:rows]
+    sel = torch.zeros(n, dtype=torch.bool, device=dev)
+    sel[pick] = True
+    m = sel[edges[:, 1]]
+    src = edges[m, 0].cpu().numpy()
+    dst = edges[m, 1].cpu().numpy()
+    fn, asn, adn = f.cpu().numpy(), a_s.cpu().numpy(), a_d.cpu().numpy()
+    order = np.argsort(dst, kind="stable")
+    src, dst = src[order], dst[order]
+    lg = asn[src] + adn[dst]
+    lg = np.where(lg >= 0, lg, np.float32(0.2) * lg).astype(np.float32)
+    want = np.zeros((n, H, Dh), np.float32)
+    bounds = np.flatnonzero(np.r_[True, dst[1:] != dst[:-1], True])
+    for i in range(len(bounds) - 1):
+        lo, hi = bounds[i], bounds[i + 1]
+        l = lg[lo:hi]
+        ex = np.exp(l - l.max(axis=0, keepdims=True))
+        al = (ex / ex.sum(axis=0, keepdims=True)).astype(np.float32)
+        want[dst[lo]] = (fn[src[lo:hi]] * al[:, :, None]).sum(axis=0)
+    pk = pick.cpu().numpy()
+    return parity_stats(got.reshape(n, H * Dh)[pick].cpu().numpy(), want[pk].reshape(len(pk), H * Dh))
+
+
+# ------------------------------------------------------------------------------------------
+# cfg4: 3 x GraphSageConv(mean) 100 -> 128 -> 128 -> 47, products-shape stand-in (BASELINE.json configs[3])
+# ------------------------------------------------------------------------------------------
+
+def bench_sage(args, torch, dist, pgl, ops, GF, dev, world, rank):
+    n, und = 2_449_029, 61_859_140
+    hbm_gbs, peak_src = peaks()
+    half = gen_edges(torch, n, und, 0.6, 5, dev)
+    edges = torch.cat([half, half.flip(1)], 0)
+    del half
+    e = int(edges.shape[0])
+    x = gen_features(torch, n, 100, 4, dev)
+    dims = [100, 128, 128, 47]
+    torch.manual_seed(6)
+    layers = [pgl.nn.GraphSageConv(dims[i], dims[i + 1], aggr_func="mean").to(dev) for i in range(3)]
+    if world > 1:
+        return bench_sage_sharded(args, torch, dist, pgl, ops, dev, world, rank, edges, x, layers, dims, n, e)
+    g = pgl.Graph(edges=edges, num_nodes=n)
+    fwd = g._fwd_csr()
+
+    def forward():
+        h = x
+        for i, conv in enumerate(layers):
+            h = conv(g, h, act="relu" if i < 2 else None)
+        return h
+
+    per_layer = []
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            forward()
+        sampler = ClockSampler(dev.index)
+        sampler.start()
+        l0 = ops.launch_count()
+        total_ms, per = timed_steps(torch, forward, args.steps)
+        launches = ops.launch_count() - l0
+        clocks = sampler.stop()
+        h = x
+        for i, conv in enumerate(layers):
+            d = dims[i]
+            agg = lambda: g.send_recv(h, "mean")   # noqa: E731
+            for _ in range(3):
+                agg()
+            t_ms, p_ = timed_steps(torch, agg, 5)
+            b_alg = e * (4 * d + 8) + n * 4 * d + (n + 1) * 8
+            per_layer.append({"in": d, "out": dims[i + 1], "aggregation_ms": t_ms / 5,
+                              "agg_alg_GBs": b_alg / (t_ms / 5) / 1e6,
+                              "agg_roofline_frac": b_alg / (t_ms / 5) / 1e6 / hbm_gbs})
+            h = conv(g, h, act="relu" if i < 2 else None)
+        parity = None
+        if not args.no_cpu:
+            try:
+                k = 20000
+                lib = _load_oracle_c()
+                m = edges[:, 1] < k
+                src_np = np.ascontiguousarray(edges[m, 0].cpu().numpy())
+                dst_np = np.ascontiguousarray(edges[m, 1].cpu().numpy())
+                x_np = x.cpu().numpy()
+                want = np.empty((k, 100), np.float32)
+                lib.orc_send_u_recv_f32(_ptr(x_np), _ptr(src_np), _ptr(dst_np), _i64(len(src_np)), _i64(k), _i64(100), 1,
+                                        _ptr(want))
+                parity = parity_stats(g.send_recv(x, "mean")[:k].cpu().numpy(), want)
+                parity["what"] = "layer-1 mean aggregation (400-byte rows), rows dst < %d vs oracle_c" % k
+            except Exception as ex:
+                parity = {"pass": None, "error": repr(ex)[:300]}
+    ms_step = total_ms / args.steps
+    agg0 = per_layer[0]
+    return {
+        "metric": "edges/sec per GraphSAGE forward (3 layers, mean aggregation)", "value": 3 * e / (ms_step * 1e-3),
+        "unit": "edges/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg4 ogbn-products-shape stand-in (Chung-Lu exp 0.6, symmetrised): %d nodes / %d directed "
+                               "edges, X [N,100] f32; 3 x GraphSageConv(mean) 100->128->128->47, full-batch forward" % (n, e),
+                   "max_in_degree": int(fwd["max_degree"]), "layers": per_layer,
+                   "sector_note": "400-byte rows start on 16-byte, not 128-byte, boundaries: a row touches 13 or 14 "
+                                  "32-byte sectors for 12.5 useful (sector efficiency 0.89-0.96)"},
+        "roofline": {"bound": "hbm", "achieved": agg0["agg_alg_GBs"], "peak": hbm_gbs, "unit": "GB/s",
+                     "frac": agg0["agg_roofline_frac"], "traffic": read_traffic("sage_l1_bytes_per_launch"),
+                     "peak_source": peak_src, "kernel": kernel_name(),
+                     "note": "layer-1 mean aggregation (D = 100): E*(4D+8) + N*4D + (N+1)*8 = 416 B/edge model"},
+        "parity": parity, "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+    }
+
+
+def bench_sage_sharded(args, torch, dist, pgl, ops, dev, world, rank, edges, x, layers, dims, n, e):
+    """cfg4 as north_star states it: METIS world-way row partition + halo exchange per layer (ShardedGraph),
+    every rank owning its nodes' rows."""
+    from pgl_b200.distributed import ShardedGraph
+    hbm_gbs, peak_src = peaks()
+    method = args.partition
+    sg = ShardedGraph.from_global_edges(edges, n, world, rank, method=method, mode=args.halo, overlap=args.overlap)
+    owned = sg.owned_global_ids()
+    for conv in layers:   # same weights on every rank
+        for p in conv.parameters():
+            dist.broadcast(p.data, 0)
+    bufs = {}
+
+    import torch.nn.functional as F
+    x_own = x[owned].contiguous()
+
+    def forward():
+        h = x_own
+        for i, conv in enumerate(layers):
+            d = dims[i]
+            if d not in bufs:
+                bufs[d] = sg.features(d)
+            x_ext, x_local = bufs[d]
+            x_local.copy_(h)
+            neigh = sg.send_recv(x_local, "mean")            # halo exchange + local mean aggregation
+            h = conv.self_linear(h) + conv.neigh_linear(neigh)   # reference pgl/nn/conv.py:106-115
+            if i < 2:
+                h = F.relu(h)
+            h = F.normalize(h, dim=1)
+        return h
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            forward()
+        sampler = ClockSampler(dev.index)
+        sampler.start()
+        l0 = ops.launch_count()
+        total_ms, per = timed_steps(torch, forward, args.steps, dist)
+        launches = ops.launch_count() - l0
+        clocks = sampler.stop()
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    stats = sg.stats()
+    allstats = [None] * world
+    dist.all_gather_object(allstats, stats)
+    return {
+        "metric": "edges/sec per GraphSAGE forward (3 layers, mean aggregation)", "value": 3 * e / (ms_step * 1e-3),
+        "unit": "edges/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg4 products-shape stand-in, %d nodes / %d directed edges, 3 x GraphSageConv(mean)" % (n, e),
+                   "parallelism": "%d-way %s row partition + halo exchange (%s) per layer" % (world, method, sg.mode),
+                   "per_rank": allstats},
+        "roofline": {"bound": "hbm", "achieved": None, "peak": hbm_gbs, "unit": "GB/s", "frac": None, "traffic": None,
+                     "peak_source": peak_src, "note": "multi-layer sharded forward: see per_rank for halo sizes"},
+        "parity": None, "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
     }
 
 

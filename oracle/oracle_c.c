@@ -155,6 +155,25 @@ int orc_segment_pool_f32(const float *data, const int64_t *ids, int64_t E, int64
     return 0;
 }
 
+/* `feature * norm` and `output * norm` of GCNConv.forward (pgl/nn/conv.py:242,250): an elementwise
+ * multiply with the [N, 1] degree norm broadcast along the feature axis (Paddle's elementwise_mul CPU
+ * contract: out[i, k] = x[i, k] * s[i], one rounding).  In place when out == x.  Rows are independent, so
+ * the threaded form is bit-identical to the sequential one. */
+int orc_scale_rows_f32(const float *x, const float *s, int64_t n, int64_t D, float *out, int nthreads) {
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+    (void)nthreads;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        const float si = s[i];
+        const float *xi = x + i * D;
+        float *oi = out + i * D;
+        for (int64_t k = 0; k < D; ++k) oi[k] = xi[k] * si;
+    }
+    return 0;
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -38,7 +38,8 @@ def _sources():
 
 
 def _deps():
-    return _sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(ROOT, "include", "pglb.h")]
+    return _sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.inl")) + \
+        [os.path.join(ROOT, "include", "pglb.h")]
 
 
 def _stale(target, deps):
@@ -55,7 +56,8 @@ def build_lib(force=False, verbose=False):
     os.makedirs(bdir, exist_ok=True)
     objs = []
     procs = []
-    hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(ROOT, "include", "pglb.h")]
+    hdrs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.inl")) + \
+        [os.path.join(ROOT, "include", "pglb.h")]
     for s in _sources():
         o = os.path.join(bdir, os.path.basename(s) + ".o")
         objs.append(o)

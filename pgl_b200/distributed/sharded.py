@@ -87,6 +87,16 @@ class ShardedGraph(object):
         self.new_id = new_id
         return self
 
+    def owned_global_ids(self):
+        """ORIGINAL (pre-relabel) global id of every owned row, in local row order (int64 tensor on the
+        shard's device): row i of this rank's features / outputs is node owned_global_ids()[i]."""
+        lo, hi = self.plan.lo, self.plan.hi
+        if getattr(self, "new_id", None) is None:
+            return torch.arange(lo, hi, dtype=torch.int64, device=self.device)
+        perm = np.empty(len(self.new_id), dtype=np.int64)
+        perm[self.new_id] = np.arange(len(self.new_id), dtype=np.int64)   # new id -> original id
+        return torch.from_numpy(perm[lo:hi]).to(self.device)
+
     # ------------------------------------------------------------------ feature buffers
     def features(self, dim):
         """(x_ext [n_local + n_halo, dim], x_local view of its first n_local rows).  Keep node

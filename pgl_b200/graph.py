@@ -364,22 +364,32 @@ class Graph(object):
         return ops.aggregate_copy(feature, fwd, n_out, reduce_op, bwd=bwd, scale_src=scale_src,
                                   scale_dst=scale_dst)
 
+    def host_aggregator(self, num_rows, dim, chunks=2, depth=2):
+        """The cached ``ops.HostAggregator`` of this graph for [num_rows, dim] float32 host matrices
+        (``submit`` / ``wait`` pipeline successive calls; see its docstring for the buffer contract)."""
+        if not self._is_tensor:
+            raise ValueError("You must call Graph.tensor()")
+        key = ("_host_agg", int(num_rows), int(dim), int(chunks), int(depth))
+        agg = self.__dict__.get("_host_agg_cache", {}).get(key)
+        if agg is None:
+            agg = ops.HostAggregator(self._fwd_csr(), int(num_rows), self._n, int(dim), self._edges.device,
+                                     chunks, depth)
+            self.__dict__.setdefault("_host_agg_cache", {})[key] = agg
+        return agg
+
     def send_recv_host(self, feature_host, out_host=None, reduce_func="sum", scale_src=None,
                        scale_dst=None, chunks=2):
         """``send_recv`` for a feature matrix in pinned HOST memory (result in pinned host memory):
         the graph stays resident, the features stream through the GPU in column chunks with upload,
-        aggregation and download overlapped (``ops.HostAggregator``).  Not in the reference (its
+        aggregation and download overlapped (``ops.HostAggregator``).  BLOCKING: when it returns,
+        ``out_host`` holds the result and ``feature_host`` may be rewritten.  Not in the reference (its
         tensors are device-resident); this is the host-buffer entry the end-to-end number uses."""
         if not self._is_tensor:
             raise ValueError("You must call Graph.tensor()")
         assert reduce_func in ["sum", "mean", "max", "min"], \
             "Only support 'sum', 'mean', 'max', 'min' built-in reduce functions."
         n, d = int(feature_host.shape[0]), int(feature_host.shape[1])
-        key = ("_host_agg", n, d, int(chunks))
-        agg = self.__dict__.get("_host_agg_cache", {}).get(key)
-        if agg is None:
-            agg = ops.HostAggregator(self._fwd_csr(), n, self._n, d, self._edges.device, chunks)
-            self.__dict__.setdefault("_host_agg_cache", {})[key] = agg
+        agg = self.host_aggregator(n, d, chunks, depth=1)
         if out_host is None:
             out_host = torch.empty((self._n, d), dtype=torch.float32, pin_memory=True)
         return agg(feature_host, out_host, reduce_func, scale_src, scale_dst)

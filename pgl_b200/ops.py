@@ -172,52 +172,101 @@ def _copy2d(dst_ptr, dpitch, src_ptr, spitch, width, height, kind, stream):
 class HostAggregator(object):
     """send_u_recv for features that live in (pinned) HOST memory: out_host = aggregate(x_host).
 
-    The graph stays resident on the GPU; per call the [N, D] float32 matrix is streamed through
-    the GPU in `chunks` column blocks on three streams -- upload of block c+1, aggregation of block
-    c and download of block c-1 run concurrently (PCIe is full duplex, and the columns of a
-    copy-message aggregation are independent) -- so a call costs about one direction of PCIe
-    traffic instead of two plus the kernel."""
+    The graph stays resident on the GPU; per call the [N, D] float32 matrix is streamed through the GPU
+    in `chunks` column blocks on three streams -- upload of block c+1, aggregation of block c and
+    download of block c-1 run concurrently (PCIe is full duplex, and the columns of a copy-message
+    aggregation are independent).
 
-    def __init__(self, fwd, n_src, n_dst, dim, device, chunks=2):
+    Two ways to call it:
+
+    * ``agg(x_host, out_host, ...)``  BLOCKING: returns when ``out_host`` holds the result (the host
+      thread has waited for the last device-to-host copy), so the caller may read ``out_host`` and
+      rewrite ``x_host`` immediately.
+    * ``t = agg.submit(x_host, out_host, ...)`` ... ``agg.wait(t)``  PIPELINED across calls: the
+      aggregator owns ``depth`` device buffer sets, so the upload of call i+1 overlaps the kernel and
+      the download of call i (a stream of feature matrices costs one direction of PCIe traffic per
+      matrix).  Contract: ``x_host`` must not be written and ``out_host`` must not be read until
+      ``wait(t)`` (or ``t.synchronize()``) has returned."""
+
+    def __init__(self, fwd, n_src, n_dst, dim, device, chunks=2, depth=2):
         self.fwd, self.n_src, self.n_dst, self.dim = fwd, int(n_src), int(n_dst), int(dim)
         self.device = device
         chunks = max(1, min(int(chunks), self.dim // 4 if self.dim >= 4 else 1))
         w = -(-self.dim // chunks)
         w = (w + 3) // 4 * 4
         self.bounds = [(c, min(c + w, self.dim)) for c in range(0, self.dim, w)]
-        self.xd = torch.empty((self.n_src, self.dim), dtype=torch.float32, device=device)
-        self.od = torch.empty((self.n_dst, self.dim), dtype=torch.float32, device=device)
+        self.depth = max(1, int(depth))
+        self.sets = [None] * self.depth       # device buffer sets, allocated on first use
+        self.count = 0
         self.s_in = torch.cuda.Stream(device=device)
+        self.s_k = torch.cuda.Stream(device=device)
         self.s_out = torch.cuda.Stream(device=device)
 
-    def __call__(self, x_host, out_host, reduce_op="sum", scale_src=None, scale_dst=None):
+    def _set(self, i):
+        st = self.sets[i]
+        if st is None:
+            st = {"xd": torch.empty((self.n_src, self.dim), dtype=torch.float32, device=self.device),
+                  "od": torch.empty((self.n_dst, self.dim), dtype=torch.float32, device=self.device),
+                  "kernel_done": None, "d2h_done": None}
+            self.sets[i] = st
+        return st
+
+    def submit(self, x_host, out_host, reduce_op="sum", scale_src=None, scale_dst=None):
         assert x_host.dtype == torch.float32 and out_host.dtype == torch.float32
         assert tuple(x_host.shape) == (self.n_src, self.dim) and x_host.is_contiguous()
         assert tuple(out_host.shape) == (self.n_dst, self.dim) and out_host.is_contiguous()
+        st = self._set(self.count % self.depth)
+        self.count += 1
         main = torch.cuda.current_stream(self.device)
-        self.s_in.wait_stream(main)
-        self.s_out.wait_stream(main)
+        self.s_k.wait_stream(main)  # the scale vectors may have been produced on the caller's stream
+        if st["kernel_done"] is not None:
+            self.s_in.wait_event(st["kernel_done"])   # the previous user of this xd has been aggregated
+        if st["d2h_done"] is not None:
+            self.s_k.wait_event(st["d2h_done"])       # the previous result has left this od
+        xd, od = st["xd"], st["od"]
         pitch = self.dim * 4
-        ev_in, ev_done = [], []
+        full = len(self.bounds) == 1
         with torch.cuda.device(self.device):
+            ev_in = []
             for lo, hi in self.bounds:
-                _copy2d(self.xd.data_ptr() + lo * 4, pitch, x_host.data_ptr() + lo * 4, pitch,
-                        (hi - lo) * 4, self.n_src, 1, self.s_in.cuda_stream)
+                if full:
+                    with torch.cuda.stream(self.s_in):
+                        xd.copy_(x_host, non_blocking=True)
+                else:
+                    _copy2d(xd.data_ptr() + lo * 4, pitch, x_host.data_ptr() + lo * 4, pitch,
+                            (hi - lo) * 4, self.n_src, 1, self.s_in.cuda_stream)
                 e = torch.cuda.Event()
                 e.record(self.s_in)
                 ev_in.append(e)
             for i, (lo, hi) in enumerate(self.bounds):
-                main.wait_event(ev_in[i])
-                _spmm_raw(self.fwd["indptr"], self.fwd["cols"], self.xd[:, lo:hi], self.n_dst, reduce_op,
-                          scale_src=scale_src, scale_dst=scale_dst,
-                          max_degree=self.fwd.get("max_degree", -1), out=self.od[:, lo:hi],
-                          packed=_packed_of(self.fwd, self.xd[:, lo:hi]))
+                self.s_k.wait_event(ev_in[i])
+                with torch.cuda.stream(self.s_k):
+                    _spmm_raw(self.fwd["indptr"], self.fwd["cols"], xd[:, lo:hi], self.n_dst, reduce_op,
+                              scale_src=scale_src, scale_dst=scale_dst,
+                              max_degree=self.fwd.get("max_degree", -1), out=od[:, lo:hi],
+                              packed=_packed_of(self.fwd, xd[:, lo:hi]))
                 e = torch.cuda.Event()
-                e.record(main)
+                e.record(self.s_k)
                 self.s_out.wait_event(e)
-                _copy2d(out_host.data_ptr() + lo * 4, pitch, self.od.data_ptr() + lo * 4, pitch,
-                        (hi - lo) * 4, self.n_dst, 2, self.s_out.cuda_stream)
-        main.wait_stream(self.s_out)
+                if full:
+                    with torch.cuda.stream(self.s_out):
+                        out_host.copy_(od, non_blocking=True)
+                else:
+                    _copy2d(out_host.data_ptr() + lo * 4, pitch, od.data_ptr() + lo * 4, pitch,
+                            (hi - lo) * 4, self.n_dst, 2, self.s_out.cuda_stream)
+                st["kernel_done"] = e
+        done = torch.cuda.Event()
+        done.record(self.s_out)
+        st["d2h_done"] = done
+        return done
+
+    def wait(self, ticket):
+        ticket.synchronize()
+
+    def __call__(self, x_host, out_host, reduce_op="sum", scale_src=None, scale_dst=None):
+        t = self.submit(x_host, out_host, reduce_op, scale_src, scale_dst)
+        torch.cuda.current_stream(self.device).wait_event(t)
+        t.synchronize()  # the host may touch out_host / x_host as soon as this returns
         return out_host
 
 
@@ -893,3 +942,15 @@ def degree_norm(degree):
 
 def launch_count():
     return _lib.launch_count()
+
+
+def stream_kernel_name():
+    """Which wide-row streaming kernel pglb_spmm_csr_f32 routes copy-sum aggregations to (PGLB_STREAM_V5,
+    read once per process by the library; mirrors csrc/spmm_v5.inl v5_mode())."""
+    v = os.environ.get("PGLB_STREAM_V5", "1")
+    geo = {"0": "GRP=4,NG=4,W=13", "1": "GRP=8,NG=4,W=6", "2": "GRP=8,NG=3,W=9"}.get(os.environ.get("PGLB_V5_GEO", "0"),
+                                                                                 "GRP=4,NG=4,W=13")
+    if v == "0":
+        return "spmm_stream128_kernel<RK=0,SCALED=1,PK=2,YM=0,CFG=1> (+ task_plan, empty_rows, fix-up kernels)"
+    how = "TMA tile::gather4 (UTMALDG.2D.GATHER4)" if v != "2" else "LDGSTS ring"
+    return "spmm_v5_kernel<%s, %s> (+ task_plan, empty_rows, fix-up kernels)" % (how, geo)

@@ -30,10 +30,11 @@ def sample_neighbors(row, colptr, input_nodes, sample_size=-1, eids=None, return
     total = int(offsets[n].item())
     neighbors = torch.empty(total, dtype=torch.int64, device=dev)
     out_eids = torch.empty(total, dtype=torch.int64, device=dev) if return_eids else None
-    with torch.cuda.device(dev):
-        check(lib.pglb_sample_fill(p(colptr), p(row), p(eids), p(nodes), n, int(sample_size),
-                                   int(seed) & 0xFFFFFFFFFFFFFFFF, p(offsets), p(neighbors), p(out_eids),
-                                   stream))
+    if total > 0:  # sample_size == 0 (or no neighbours at all): nothing to fill, and an empty tensor has no address
+        with torch.cuda.device(dev):
+            check(lib.pglb_sample_fill(p(colptr), p(row), p(eids), p(nodes), n, int(sample_size),
+                                       int(seed) & 0xFFFFFFFFFFFFFFFF, p(offsets), p(neighbors), p(out_eids),
+                                       stream))
     neighbors._pglb_offsets = offsets  # rides along for reindex_graph (saves a scan)
     if return_eids:
         return neighbors, count, out_eids

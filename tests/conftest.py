@@ -23,6 +23,22 @@ def pytest_configure(config):
         obuild.build_ref()
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests need a CUDA device: skip them (instead of erroring) on a CPU box, so a plain
+    `pytest tests/` is clean everywhere."""
+    try:
+        import torch
+        has_cuda = torch.cuda.is_available()
+    except Exception:
+        has_cuda = False
+    if has_cuda:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def kat():
     import json

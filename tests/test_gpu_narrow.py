@@ -1,12 +1,12 @@
-"""GPU tests of the EXPERIMENTAL narrow-row streaming kernel (csrc/spmm_stream.cu, spmm_narrow_kernel:
-rows of <= 64 floats, 2 / 4 / 8 slots per warp step -- the kernel behind the column-sharded multi-GPU
-layout).  GATED: never run on hardware yet.  Run in its own process:
+"""GPU tests of the narrow-row streaming kernel (csrc/spmm_stream.cu, spmm_narrow_kernel: rows of <= 64
+floats, 2 / 4 / 8 slots per warp step -- the kernel behind the column-sharded multi-GPU layout).  Validated on
+a B200 in round 2's first GPU call; the narrow path is on by default (PGLB_NARROW=0 turns it off).
 
-    PGLB_EXPERIMENTAL=1 PGLB_NARROW=1 python -m pytest tests/test_gpu_narrow.py -q
-    PGLB_EXPERIMENTAL=1 PGLB_NARROW=1 PGLB_STREAM_TASK=64 python -m pytest tests/test_gpu_narrow.py -q   # cut rows
+The task size is read once per process by the library, so the cut-row variant (PGLB_STREAM_TASK=64: rows cut by
+task boundaries everywhere) runs this file again in a child process.
 
-(the env switches are read once per process by the library).  Sum order differs from the sequential
-oracle (per-sub partial sums + tree), so the bar is the fp32 tolerance, not bit equality."""
+Sum order differs from the sequential oracle (per-sub partial sums + tree), so the bar is the fp32 tolerance,
+not bit equality."""
 import os
 
 import numpy as np
@@ -15,9 +15,7 @@ import torch
 
 from oracle import oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PGLB_EXPERIMENTAL") != "1" or os.environ.get("PGLB_NARROW") != "1",
-                                 reason="experimental narrow-row kernel: set PGLB_EXPERIMENTAL=1 PGLB_NARROW=1")]
+pytestmark = pytest.mark.gpu
 RTOL = 1e-4
 
 
@@ -89,3 +87,16 @@ def test_narrow_scaled_and_accumulate(pgl):
     ed = dev(edges)
     torch.zeros(n, d, device="cuda").index_add_(0, ed[:, 1], x2[ed[:, 0]]).backward(go)
     assert rel_err(x1.grad.cpu().numpy(), x2.grad.cpu().numpy()) <= RTOL
+
+
+def test_cut_rows_in_child_process():
+    """The same tests with 64-slot tasks (every long row is cut; partials + fix-up do the work)."""
+    import subprocess
+    import sys
+    if os.environ.get("PGLB_NARROW_CHILD") == "1":
+        pytest.skip("already the child")
+    env = dict(os.environ, PGLB_STREAM_TASK="64", PGLB_NARROW_CHILD="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu",
+                        "-p", "no:cacheprovider"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]

@@ -820,23 +820,39 @@ def test_udf_path_backward(pgl):
 
 
 def test_send_recv_host_pipelined(pgl):
-    """Host-buffer entry: column-chunked upload / aggregate / download == resident result."""
+    """Host-buffer entry: column-chunked upload / aggregate / download == resident result.  The call is
+    BLOCKING: the host buffer is read right after it returns, with no caller-side sync."""
     n, e, d = 30000, 400000, 128
     edges = O.chung_lu_edges(n, e, exponent=0.9, seed=211)
     g = make_graph(pgl, edges, n)
     x = torch.randn(n, d)
     xh = x.pin_memory()
     norm = torch.rand(n, device="cuda") + 0.5
-    ref = g._send_u_recv(x.cuda(), "sum", None, scale_src=norm, scale_dst=norm)
+    ref = g._send_u_recv(x.cuda(), "sum", None, scale_src=norm, scale_dst=norm).cpu().numpy()
     for chunks in (1, 2, 4, 5):
-        oh = torch.empty(n, d).pin_memory()
+        oh = torch.full((n, d), float("nan")).pin_memory()
         g.send_recv_host(xh, oh, "sum", scale_src=norm, scale_dst=norm, chunks=chunks)
-        torch.cuda.synchronize()
-        assert rel_err(oh.numpy(), ref.cpu().numpy()) <= RTOL, chunks
+        assert rel_err(oh.numpy(), ref) <= RTOL, chunks
     oh = g.send_recv_host(xh, None, "mean")
-    torch.cuda.synchronize()
     want = O.send_u_recv(x.numpy(), edges[:, 0], edges[:, 1], "mean")
     assert rel_err(oh.numpy(), want) <= RTOL
+
+
+def test_host_aggregator_submit_wait(pgl):
+    """Pipelined use: several matrices in flight over two device buffer sets; every result is the
+    aggregation of ITS input (no buffer of an earlier call is overwritten too early)."""
+    n, e, d = 20000, 250000, 64
+    edges = O.chung_lu_edges(n, e, exponent=0.9, seed=212)
+    g = make_graph(pgl, edges, n)
+    agg = g.host_aggregator(n, d, chunks=1, depth=2)
+    xs = [torch.randn(n, d).pin_memory() for _ in range(5)]
+    outs = [torch.full((n, d), float("nan")).pin_memory() for _ in range(5)]
+    tickets = [agg.submit(xs[i], outs[i], "sum") for i in range(5)]
+    for t in tickets:
+        agg.wait(t)
+    for i in range(5):
+        want = O.send_u_recv(xs[i].numpy(), edges[:, 0], edges[:, 1], "sum")
+        assert rel_err(outs[i].numpy(), want) <= RTOL, i
 
 
 @pytest.mark.parametrize("rop", ["sum", "mean", "max", "min"])

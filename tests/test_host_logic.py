@@ -63,8 +63,27 @@ def test_gen_edges_and_bytes_model():
     # 572 B/edge at D=128, N/E = 0.1 (+ the two norm vectors)
     b = bench.algorithmic_bytes(10_000_000, 100_000_000, 128)
     assert abs(b / 100_000_000 - 572.8) < 0.1
-    n_s, src, dst = bench.cpu_sample_problem(e.numpy(), 1000, 0.1)
-    assert n_s == 100 and (dst < 100).all() and len(src) == len(dst)
+    # the CPU arm's row sample: rows dst < n_s with ALL their in-edges; the GCN restatement on it equals numpy
+    en = e.numpy()
+    src, dst = np.ascontiguousarray(en[:, 0]), np.ascontiguousarray(en[:, 1])
+    lib = bench._load_oracle_c()
+    prob = bench.CpuGcn(lib, src, dst, 1000, 8, 0.1, threads=2)
+    assert prob.n_s == 100 and (prob.dst < 100).all() and prob.e_s == int((dst < 100).sum())
+    x = np.random.default_rng(1).standard_normal((1000, 8)).astype(np.float32)
+    norm = bench.cpu_norm(np.bincount(dst, minlength=1000))
+    for threads in (1, 2):
+        t, det = prob.run(x, norm, threads)
+        want = np.zeros((100, 8), np.float32)
+        xs = x * norm[:, None]
+        for s_, d_ in zip(prob.src, prob.dst):
+            want[d_] += xs[s_]
+        want *= norm[:100, None]
+        assert np.array_equal(prob.out, want) and t > 0 and det["sample_edges"] == prob.e_s
+    st = bench.parity_stats(prob.out, want)
+    assert st["pass"] and st["bit_exact_rows"] == 100 and st["max_rel_err"] == 0.0
+    bad = want.copy()
+    bad[3, 2] += 1.0
+    assert not bench.parity_stats(bad, want)["pass"]
 
 
 def test_relabel_matches_reference_graph_kernel():
