@@ -143,6 +143,25 @@ int pglb_spmm_csr_f32(const int64_t *indptr, const int64_t *cols, const int64_t 
 int pglb_pack_cols(const int64_t *cols, int64_t num_edges, int64_t n_src, int32_t *count,
                    int64_t min_count, uint32_t *packed, void *stream);
 
+/* Narrow-row copy aggregation (sum / mean, D = 4..64 floats, D % 4 == 0): the same send_u_recv
+ * (pgl/graph.py:860,886) for the 16..256-byte rows of a COLUMN-sharded feature matrix (every GPU holds the whole
+ * CSR and D/R columns; reference precedent for the layout: examples/.../dist_feat.py:31-49).
+ * pglb_narrow_plan builds, once per graph, what the kernel streams instead of cols/indptr:
+ *   plan[E]        uint32: cols[j] | (slot j is the first of its row) << 30   (needs n_src < 2^30)
+ *   nz_row[n_dst+2] int32: ids of the non-empty rows in order, padded with two copies of the last one
+ *   blk_k[ceil(E/32)] int32: index into nz_row of the row that owns slot 32 b - 1 (-1 for b = 0)
+ * ws: pglb_narrow_plan_ws(n_dst) / pglb_spmm_narrow_ws(E, D).  x and out rows 16-byte aligned (ldx, ldo % 4 == 0).
+ * Row sums are formed in slot order inside 32-slot ranges and the ranges of a row added left to right:
+ * deterministic, equal to the sequential loop up to fp32 rounding of the regrouping. */
+int pglb_narrow_plan_ws(int64_t n_dst, size_t *ws_bytes);
+int pglb_narrow_plan(const int64_t *indptr, const int64_t *cols, int64_t n_dst, int64_t n_src, int64_t num_edges,
+                     uint32_t *plan, int32_t *nz_row, int32_t *blk_k, void *ws, size_t ws_bytes, void *stream);
+int pglb_spmm_narrow_ws(int64_t num_edges, int64_t D, size_t *ws_bytes);
+int pglb_spmm_narrow_f32(const uint32_t *plan, const int32_t *nz_row, const int32_t *blk_k, const int64_t *indptr,
+                         const float *x, int64_t ldx, float *out, int64_t ldo, int64_t n_dst, int64_t n_src,
+                         int64_t num_edges, int64_t D, int reduce_op, const float *scale_src, const float *scale_dst,
+                         void *ws, size_t ws_bytes, void *stream);
+
 /* ------------------------------------------------------------------------------------
  * Edge-parallel ops
  * ---------------------------------------------------------------------------------- */

@@ -400,6 +400,62 @@ __global__ void __launch_bounds__(256) segment_indptr_kernel(const int64_t *ids,
     }
 }
 
+
+// ---- plan of the narrow-row aggregation (csrc/spmm_narrow2.inl) ----------------------------------------------
+// plan[j] = cols[j] | (slot j starts a row) << 30 ; nz_row[k] = id of the k-th non-empty row (padded with two
+// copies of the last one) ; blk_k[b] = k of the row that owns slot 32 b - 1 (-1 for b = 0).
+__global__ void __launch_bounds__(256) plan_cols_kernel(const int64_t *__restrict__ cols, int64_t E,
+                                                        uint32_t *__restrict__ plan) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < E) plan[j] = (uint32_t)cols[j];
+}
+__global__ void __launch_bounds__(256) plan_rows_kernel(const int64_t *__restrict__ indptr, int64_t N,
+                                                        const int64_t *__restrict__ rank,
+                                                        uint32_t *__restrict__ plan, int32_t *__restrict__ nz_row) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    const int64_t b = indptr[r], e = indptr[r + 1];
+    if (e > b) {
+        nz_row[rank[r]] = (int32_t)r;
+        plan[b] |= 0x40000000u;
+    }
+    if (r == N - 1) {  // pad: the kernel reads nz_row[k + 1] one row ahead
+        const int64_t K = rank[r] + (e > b ? 1 : 0);
+        // the last non-empty row is the one that owns the last slot; with K == 0 there is nothing to read
+        int64_t last = 0;
+        if (K > 0) {
+            int64_t lo = 0, hi = N;  // upper_bound(indptr, E - 1) - 1
+            const int64_t v = indptr[N] - 1;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (indptr[mid] > v) hi = mid;
+                else lo = mid + 1;
+            }
+            last = lo - 1;
+        }
+        nz_row[K] = (int32_t)last;
+        nz_row[K + 1] = (int32_t)last;
+    }
+}
+__global__ void __launch_bounds__(256) plan_blocks_kernel(const int64_t *__restrict__ indptr, int64_t N,
+                                                          const int64_t *__restrict__ rank, int64_t nblk,
+                                                          int32_t *__restrict__ blk_k) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    if (b == 0) {
+        blk_k[0] = -1;
+        return;
+    }
+    const int64_t v = b * 32 - 1;  // the slot just before the block: which row owns it?
+    int64_t lo = 0, hi = N;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg((const long long *)indptr + mid) > v) hi = mid;
+        else lo = mid + 1;
+    }
+    blk_k[b] = (int32_t)rank[lo - 1];
+}
+
 }  // namespace pglb
 
 using namespace pglb;
@@ -487,5 +543,43 @@ extern "C" int pglb_segment_indptr(const int64_t *segment_ids, int64_t E, int64_
     const int blocks = (int)std::min<int64_t>((E + 256) / 256, (int64_t)sm_count() * 16);
     segment_indptr_kernel<<<blocks, 256, 0, stream>>>(segment_ids, E, K, indptr);
     PGLB_LAUNCH_CHECK("segment_indptr_kernel");
+    return PGLB_OK;
+}
+
+
+extern "C" int pglb_narrow_plan_ws(int64_t N, size_t *ws_bytes) {
+    PGLB_CHECK_ARG(ws_bytes && N >= 0, PGLB_EINVAL, "pglb_narrow_plan_ws: bad argument");
+    *ws_bytes = align_up(sizeof(int64_t) * (N ? N : 1), 256) * 2 + scan_ws_bytes(N);
+    return PGLB_OK;
+}
+
+extern "C" int pglb_narrow_plan(const int64_t *indptr, const int64_t *cols, int64_t N, int64_t n_src, int64_t E,
+                                uint32_t *plan, int32_t *nz_row, int32_t *blk_k, void *ws, size_t ws_bytes,
+                                void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    PGLB_CHECK_ARG(N > 0 && E > 0, PGLB_EINVAL, "pglb_narrow_plan: needs at least one row and one slot");
+    PGLB_CHECK_ARG(N < 0x7fffffffLL && n_src < 0x40000000LL, PGLB_ESHAPE,
+                   "pglb_narrow_plan: needs n_dst < 2^31 and n_src < 2^30");
+    PGLB_CHECK_ARG(indptr && cols && plan && nz_row && blk_k, PGLB_EINVAL, "pglb_narrow_plan: NULL pointer");
+    size_t need = 0;
+    pglb_narrow_plan_ws(N, &need);
+    PGLB_CHECK_ARG(ws && ws_bytes >= need, PGLB_EWORKSPACE, "pglb_narrow_plan: workspace of %zu bytes needed (got %zu)",
+                   need, ws_bytes);
+    char *base = reinterpret_cast<char *>(ws);
+    const size_t vec = align_up(sizeof(int64_t) * (size_t)N, 256);
+    int64_t *flag = reinterpret_cast<int64_t *>(base);
+    int64_t *rank = reinterpret_cast<int64_t *>(base + vec);
+    void *tmp = base + 2 * vec;
+    nonempty_flag_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(indptr, N, flag);
+    PGLB_LAUNCH_CHECK("nonempty_flag_kernel");
+    const int rc = scan_i64(flag, rank, N, /*inclusive=*/0, tmp, stream);
+    if (rc) return rc;
+    plan_cols_kernel<<<(unsigned)((E + 255) / 256), 256, 0, stream>>>(cols, E, plan);
+    PGLB_LAUNCH_CHECK("plan_cols_kernel");
+    plan_rows_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(indptr, N, rank, plan, nz_row);
+    PGLB_LAUNCH_CHECK("plan_rows_kernel");
+    const int64_t nblk = (E + 31) / 32;
+    plan_blocks_kernel<<<(unsigned)((nblk + 255) / 256), 256, 0, stream>>>(indptr, N, rank, nblk, blk_k);
+    PGLB_LAUNCH_CHECK("plan_blocks_kernel");
     return PGLB_OK;
 }

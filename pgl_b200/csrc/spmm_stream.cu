@@ -1004,6 +1004,7 @@ static int launch_narrow_pk(const StreamP &p, int pk, bool scaled, cudaStream_t 
 }
 
 #include "spmm_v5.inl"
+#include "spmm_narrow2.inl"
 
 struct StreamWs {
     int64_t *first_row;
@@ -1208,6 +1209,88 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
     return rk ? launch_stream<4, 1>(p, tiles, stream) : launch_stream<4, 0>(p, tiles, stream);
 }
 
+
+// ---- narrow2 host side --------------------------------------------------------------------------------------
+// Slots per task of the narrow kernel: the wide kernel's choice rounded up to whole chunks of (32 / LPR) * 32 slots
+static int narrow2_lpr(int64_t D) { return D <= 16 ? 4 : (D <= 32 ? 8 : 16); }
+static int64_t narrow2_task_size(int64_t E, int64_t D) {
+    const int64_t chunk = (32 / narrow2_lpr(D)) * 32;
+    const int64_t t = stream_task_size(E);
+    return (t + chunk - 1) / chunk * chunk;
+}
+size_t narrow2_ws_bytes(int64_t E, int64_t D) { return stream_layout(nullptr, E, D, narrow2_task_size(E, D)).bytes; }
+
+int narrow2_run(const uint32_t *plan, const int32_t *nz_row, const int32_t *blk_k, const int64_t *indptr, const float *x,
+                int64_t ldx, float *out, int64_t ldo, int64_t n_dst, int64_t E, int64_t D, int reduce_op,
+                const float *scale_src, const float *scale_dst, void *ws, size_t ws_bytes, cudaStream_t stream) {
+    const int64_t T = narrow2_task_size(E, D);
+    StreamWs w = stream_layout(ws, E, D, T);
+    PGLB_CHECK_ARG(ws != nullptr && ws_bytes >= w.bytes, PGLB_EWORKSPACE,
+                   "pglb_spmm_narrow_f32: workspace of %zu bytes needed (got %zu)", w.bytes, ws_bytes);
+    NarrowP p{};
+    p.plan = plan;
+    p.nz_row = nz_row;
+    p.blk_k = blk_k;
+    p.indptr = indptr;
+    p.x = x;
+    p.ldx = ldx;
+    p.out = out;
+    p.ldo = ldo;
+    p.E = E;
+    p.D = (int)D;
+    p.mean = reduce_op == PGLB_REDUCE_MEAN;
+    p.scale_src = scale_src;
+    p.scale_dst = scale_dst;
+    p.T = T;
+    p.ntasks = w.ntasks;
+    p.partial = w.partial;
+    p.dpad = w.dpad;
+    p.tail_row = w.tail_row;
+    // the shared pieces: zero-fill of empty rows before, fix-up of task-cut rows after
+    StreamP sp{};
+    sp.indptr = indptr;
+    sp.out = out;
+    sp.ldo = ldo;
+    sp.n_rows = n_dst;
+    sp.E = E;
+    sp.D = (int)D;
+    sp.reduce_op = reduce_op;
+    sp.scale_dst = scale_dst;
+    sp.T = T;
+    sp.ntasks = w.ntasks;
+    sp.partial = w.partial;
+    sp.dpad = w.dpad;
+    sp.tail_row = w.tail_row;
+    {
+        const int rc = launch_empty_rows(sp, stream);
+        if (rc) return rc;
+    }
+    const int64_t blocks = (p.ntasks + kNarrowWarps - 1) / kNarrowWarps;
+    PGLB_CHECK_ARG(blocks <= 0x7fffffffLL, PGLB_ESHAPE, "spmm_narrow2: grid too large");
+    const int lpr = narrow2_lpr(D);
+#define PGLB_N2K(L, SC, MN) spmm_narrow2_kernel<L, SC, MN><<<(unsigned)blocks, kNarrowWarps * 32, 0, stream>>>(p)
+#define PGLB_N2(L)                                              \
+    do {                                                        \
+        if (scale_src) {                                        \
+            if (p.mean) PGLB_N2K(L, true, true);                \
+            else PGLB_N2K(L, true, false);                      \
+        } else {                                                \
+            if (p.mean) PGLB_N2K(L, false, true);               \
+            else PGLB_N2K(L, false, false);                     \
+        }                                                       \
+    } while (0)
+    if (lpr == 4) PGLB_N2(4);
+    else if (lpr == 8) PGLB_N2(8);
+    else PGLB_N2(16);
+#undef PGLB_N2K
+#undef PGLB_N2
+    PGLB_LAUNCH_CHECK("spmm_narrow2_kernel");
+    const int64_t fblocks = (p.ntasks * 32 + 255) / 256;
+    spmm_stream_fixup_kernel<1, 0><<<(unsigned)fblocks, 256, 0, stream>>>(sp);
+    PGLB_LAUNCH_CHECK("spmm_stream_fixup_kernel");
+    return PGLB_OK;
+}
+
 // Single-pass GAT aggregation (inference): out[d,h,:] = sum_j softmax_j(leaky(as[src_j,h] + ad[d,h])) f[src_j,h,:]
 int gat_fused_run(const int64_t *indptr, const int64_t *cols, const float *f, int64_t ldf, float *out,
                   int64_t ldo, int64_t n_dst, int64_t n_src, int64_t E, int64_t D, int64_t H,
@@ -1258,3 +1341,30 @@ int gat_fused_run(const int64_t *indptr, const int64_t *cols, const float *f, in
 }
 
 }  // namespace pglb
+
+using namespace pglb;
+
+extern "C" int pglb_spmm_narrow_ws(int64_t num_edges, int64_t D, size_t *ws_bytes) {
+    PGLB_CHECK_ARG(ws_bytes != nullptr && num_edges >= 0 && D > 0, PGLB_EINVAL, "pglb_spmm_narrow_ws: bad argument");
+    *ws_bytes = narrow2_ws_bytes(num_edges, D);
+    return PGLB_OK;
+}
+
+extern "C" int pglb_spmm_narrow_f32(const uint32_t *plan, const int32_t *nz_row, const int32_t *blk_k,
+                                    const int64_t *indptr, const float *x, int64_t ldx, float *out, int64_t ldo,
+                                    int64_t n_dst, int64_t n_src, int64_t num_edges, int64_t D, int reduce_op,
+                                    const float *scale_src, const float *scale_dst, void *ws, size_t ws_bytes,
+                                    void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    PGLB_CHECK_ARG(n_dst > 0 && n_src > 0 && num_edges > 0, PGLB_EINVAL, "pglb_spmm_narrow_f32: empty problem");
+    PGLB_CHECK_ARG(D >= 4 && D <= 64 && D % 4 == 0, PGLB_ESHAPE, "pglb_spmm_narrow_f32: D must be 4..64, a multiple of 4");
+    PGLB_CHECK_ARG(reduce_op == PGLB_REDUCE_SUM || reduce_op == PGLB_REDUCE_MEAN, PGLB_EINVAL,
+                   "pglb_spmm_narrow_f32: sum or mean only");
+    PGLB_CHECK_ARG(plan && nz_row && blk_k && indptr && x && out, PGLB_EINVAL, "pglb_spmm_narrow_f32: NULL pointer");
+    PGLB_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (ldx % 4) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+                       (ldo % 4) == 0,
+                   PGLB_ESHAPE, "pglb_spmm_narrow_f32: x / out rows must be 16-byte aligned");
+    PGLB_CHECK_ARG(n_src < 0x40000000LL && ldx * 4 < 0xffffffffLL, PGLB_ESHAPE, "pglb_spmm_narrow_f32: n_src < 2^30 needed");
+    return narrow2_run(plan, nz_row, blk_k, indptr, x, ldx, out, ldo, n_dst, num_edges, D, reduce_op, scale_src, scale_dst,
+                       ws, ws_bytes, stream);
+}

@@ -138,6 +138,20 @@ def _spmm_raw(indptr, cols, x2, n_dst, reduce_op, eid=None, y2=None, y_bcast=BCA
     E = int(num_edges if num_edges is not None else (cols.shape[0] if cols is not None else 0))
     if out is None:
         out = torch.empty((n_dst, D), dtype=torch.float32, device=dev)
+    if isinstance(packed, NarrowPlan):
+        if (reduce_op in ("sum", "mean") and msg_op == "copy" and y2 is None and not accumulate and E > 0
+                and n_dst > 0 and x2.data_ptr() % 16 == 0 and x2.stride(0) % 4 == 0 and x2.stride(1) == 1
+                and out.data_ptr() % 16 == 0 and out.stride(0) % 4 == 0 and int(x2.shape[0]) < (1 << 30)):
+            need = ctypes.c_size_t(0)
+            check(lib.pglb_spmm_narrow_ws(E, D, ctypes.byref(need)))
+            ws = workspace(dev, need.value)
+            with torch.cuda.device(dev):
+                check(lib.pglb_spmm_narrow_f32(_ptr(packed.plan), _ptr(packed.nz_row), _ptr(packed.blk_k),
+                                               _ptr(indptr), _ptr(x2), x2.stride(0), _ptr(out), out.stride(0),
+                                               n_dst, int(x2.shape[0]), E, D, REDUCE[reduce_op], _ptr(scale_src),
+                                               _ptr(scale_dst), _ptr(ws), ws.numel(), _stream()))
+            return out
+        packed = packed.fallback() if packed.fallback is not None else None
     need = ctypes.c_size_t(0)
     check(lib.pglb_spmm_csr_ws(n_dst, E, D, ctypes.byref(need)))
     ws = workspace(dev, need.value)
@@ -409,17 +423,50 @@ class _MaxMinAgg(torch.autograd.Function):
 
 # PGLB_NARROW=1 (experimental): rows of <= 64 floats take the narrow-row streaming kernel, which reads
 # packed column ids like the wide-row kernel
-NARROW_ROWS = os.environ.get("PGLB_NARROW") == "1"
+NARROW_ROWS = os.environ.get("PGLB_NARROW", "1") != "0"      # narrow-row kernels at all (else the generic kernel)
+NARROW2 = os.environ.get("PGLB_NARROW2", "1") != "0"          # spmm_narrow2_kernel (else round 1's spmm_narrow_kernel)
+
+
+class NarrowPlan(object):
+    """What pglb_spmm_narrow_f32 streams instead of cols / indptr (see include/pglb.h); `fallback()` gives the
+    packed column ids for calls the narrow kernel does not take (max / min, accumulate, unaligned views)."""
+    __slots__ = ("plan", "nz_row", "blk_k", "fallback")
+
+    def __init__(self, plan, nz_row, blk_k, fallback=None):
+        self.plan, self.nz_row, self.blk_k, self.fallback = plan, nz_row, blk_k, fallback
+
+
+def narrow_plan(indptr, cols, n_src):
+    """Build the plan of a dst-CSR once (cached by the EdgeIndex)."""
+    require_cuda(indptr, cols)
+    dev = indptr.device
+    n_dst = int(indptr.shape[0]) - 1
+    E = int(cols.shape[0])
+    plan = torch.empty(E, dtype=torch.int32, device=dev)
+    nz_row = torch.empty(n_dst + 2, dtype=torch.int32, device=dev)
+    blk_k = torch.empty((E + 31) // 32, dtype=torch.int32, device=dev)
+    need = ctypes.c_size_t(0)
+    check(lib.pglb_narrow_plan_ws(n_dst, ctypes.byref(need)))
+    ws = workspace(dev, need.value)
+    with torch.cuda.device(dev):
+        check(lib.pglb_narrow_plan(_ptr(indptr), _ptr(cols), n_dst, int(n_src), E, _ptr(plan), _ptr(nz_row),
+                                   _ptr(blk_k), _ptr(ws), ws.numel(), _stream()))
+    return plan, nz_row, blk_k
 
 
 def _packed_of(csr, x2):
-    """Packed column ids (+ optional L2 hints) for this (graph, row width), from the EdgeIndex
-    cache; only the wide-row kernel (64 < D <= 128) consumes them."""
+    """Per-(graph, row width) index data from the EdgeIndex cache: packed column ids (+ optional L2 hints) for the
+    wide-row kernels (64 < D <= 128), the narrow plan for D <= 64."""
     fn = csr.get("packed")
     D = int(x2.shape[1])
     if fn is None or D > 128 or D % 4 or (D <= 64 and not NARROW_ROWS):
         return None
-    return fn(int(x2.shape[0]), D * 4)
+    n_src = int(x2.shape[0])
+    if D <= 64 and NARROW2 and csr.get("plan") is not None and 0 < n_src < (1 << 30) and \
+            csr["cols"] is not None and int(csr["cols"].shape[0]) > 0:
+        plan, nz_row, blk_k = csr["plan"](n_src)
+        return NarrowPlan(plan, nz_row, blk_k, fallback=lambda: fn(n_src, D * 4))
+    return fn(n_src, D * 4)
 
 
 def aggregate_copy(x, fwd, n_dst, reduce_op="sum", bwd=None, scale_src=None, scale_dst=None):

@@ -117,10 +117,18 @@ class EdgeIndex(object):
             cache[key] = ops.pack_cols(self._sorted_v, n_src, row_bytes)
         return cache[key]
 
+    def narrow_plan(self, n_src):
+        """Cached plan of the narrow-row kernel (see ops.narrow_plan): depends on the index only."""
+        cache = self.__dict__.setdefault("_plan_cache", {})
+        if "plan" not in cache:
+            cache["plan"] = ops.narrow_plan(self._indptr, self._sorted_v, n_src)
+        return cache["plan"]
+
     def csr(self):
         """dict consumed by pgl_b200.ops: rows keyed by u, columns = v, eid per slot."""
         return {"indptr": self._indptr, "cols": self._sorted_v, "eid": self._sorted_eid,
-                "degree": self._degree, "max_degree": self.max_degree, "packed": self.packed_cols}
+                "degree": self._degree, "max_degree": self.max_degree, "packed": self.packed_cols,
+                "plan": self.narrow_plan}
 
     def view_v(self, u=None):
         """reference pgl/utils/edge_index.py:103-114 (numpy mode only)."""
