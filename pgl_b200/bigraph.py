@@ -125,7 +125,7 @@ class BiGraph(object):
         """CSR keyed by source (u = src, v = dst); reference bigraph.py:528-536."""
         if self._adj_src_index is None:
             self._adj_src_index = EdgeIndex.from_edges(u=self._edges[:, 0], v=self._edges[:, 1],
-                                                       num_nodes=self._src_num_nodes)
+                                                       num_nodes=self._src_num_nodes, v_bound=self._dst_num_nodes)
         return self._adj_src_index
 
     @property
@@ -133,7 +133,7 @@ class BiGraph(object):
         """CSR keyed by destination (u = dst, v = src); reference bigraph.py:539-547."""
         if self._adj_dst_index is None:
             self._adj_dst_index = EdgeIndex.from_edges(u=self._edges[:, 1], v=self._edges[:, 0],
-                                                       num_nodes=self._dst_num_nodes)
+                                                       num_nodes=self._dst_num_nodes, v_bound=self._src_num_nodes)
         return self._adj_dst_index
 
     @property

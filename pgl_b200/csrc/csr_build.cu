@@ -133,11 +133,17 @@ static int scan_i64(const int64_t *in, int64_t *out, int64_t n, int inclusive, v
 // ---- key packing / result emission -----------------------------------------------------------
 template <typename KeyT, typename ValT>
 __global__ void __launch_bounds__(256) pack_keys_kernel(const int64_t *u, int64_t u_stride,
-                                                        int64_t E, KeyT *keys, ValT *vals,
-                                                        unsigned long long *degree) {
+                                                        int64_t E, int64_t N, KeyT *keys, ValT *vals,
+                                                        unsigned long long *degree, int *bad) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t k = u[i * u_stride];
+        if ((unsigned long long)k >= (unsigned long long)N) {  // id outside [0, N): report, never index with it
+            *bad = 1;
+            keys[i] = (KeyT)0;
+            vals[i] = (ValT)i;
+            continue;
+        }
         keys[i] = (KeyT)k;
         vals[i] = (ValT)i;
         atomicAdd(degree + k, 1ull);
@@ -287,7 +293,7 @@ struct SortGeo {
 };
 
 struct SortPlan {
-    size_t keys_a, keys_b, vals_a, vals_b, table, scan_tmp, total;
+    size_t keys_a, keys_b, vals_a, vals_b, table, scan_tmp, bad, total;
     int64_t nb;
 };
 
@@ -308,6 +314,7 @@ static SortPlan plan(int64_t E, int64_t N) {
     pl.table = take(sizeof(int64_t) * 256 * (size_t)std::max<int64_t>(pl.nb, 1));
     const int64_t longest = std::max<int64_t>(256 * std::max<int64_t>(pl.nb, 1), N);
     pl.scan_tmp = take(scan_ws_bytes(longest));
+    pl.bad = take(sizeof(int));
     pl.total = off;
     return pl;
 }
@@ -330,9 +337,17 @@ static int run(const int64_t *u, int64_t us, const int64_t *v, int64_t vs, int64
     PGLB_CUDA(cudaMemsetAsync(degree, 0, sizeof(int64_t) * N, stream));
     const int blocks = (int)std::min<int64_t>((E + 255) / 256, (int64_t)sm_count() * 16);
     if (E > 0) {
+        int *bad = reinterpret_cast<int *>(base + pl.bad);
+        PGLB_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), stream));
         pack_keys_kernel<KeyT, ValT><<<blocks, 256, 0, stream>>>(
-            u, us, E, ka, va, reinterpret_cast<unsigned long long *>(degree));
+            u, us, E, N, ka, va, reinterpret_cast<unsigned long long *>(degree), bad);
         PGLB_LAUNCH_CHECK("pack_keys_kernel");
+        // the build is graph preparation (one-off): read the range-check flag back before sorting garbage,
+        // and answer like the host twin pglb_build_index_host does
+        int bad_h = 0;
+        PGLB_CUDA(cudaMemcpyAsync(&bad_h, bad, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        PGLB_CUDA(cudaStreamSynchronize(stream));
+        PGLB_CHECK_ARG(bad_h == 0, PGLB_ESHAPE, "pglb_csr_build: a node id lies outside [0, %lld)", (long long)N);
     }
     set_first_kernel<<<1, 1, 0, stream>>>(indptr);
     PGLB_LAUNCH_CHECK("set_first_kernel");

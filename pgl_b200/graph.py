@@ -358,6 +358,8 @@ class Graph(object):
 
     def _send_u_recv(self, feature, reduce_op, out_size, scale_src=None, scale_dst=None):
         ops.require_cuda(feature)
+        if int(feature.shape[0]) < self._n:
+            raise ValueError("feature has %d rows but the graph has %d nodes" % (int(feature.shape[0]), self._n))
         n_out = self._out_rows(feature, out_size)
         fwd = self._csr_for_rows(n_out)
         bwd = self._bwd_csr if (feature.requires_grad and torch.is_grad_enabled()) else None
@@ -554,7 +556,7 @@ class Graph(object):
         """EdgeIndex keyed by src (u = src, v = dst)."""
         if self._adj_src_index is None:
             self._adj_src_index = EdgeIndex.from_edges(
-                u=self._edges[:, 0], v=self._edges[:, 1], num_nodes=self._num_nodes)
+                u=self._edges[:, 0], v=self._edges[:, 1], num_nodes=self._num_nodes, v_bound=self._n)
         return self._adj_src_index
 
     @property
@@ -562,7 +564,7 @@ class Graph(object):
         """EdgeIndex keyed by dst (u = dst, v = src)."""
         if self._adj_dst_index is None:
             self._adj_dst_index = EdgeIndex.from_edges(
-                u=self._edges[:, 1], v=self._edges[:, 0], num_nodes=self._num_nodes)
+                u=self._edges[:, 1], v=self._edges[:, 0], num_nodes=self._num_nodes, v_bound=self._n)
         return self._adj_dst_index
 
     def node_batch_iter(self, batch_size, shuffle=True):

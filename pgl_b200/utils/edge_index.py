@@ -54,10 +54,17 @@ class EdgeIndex(object):
         self._max_degree = None
 
     @classmethod
-    def from_edges(cls, u, v, num_nodes):
-        """reference pgl/utils/edge_index.py:38-58."""
+    def from_edges(cls, u, v, num_nodes, v_bound=None):
+        """reference pgl/utils/edge_index.py:38-58.  ``v_bound``: number of nodes on the v side (the kernels
+        index feature rows with v): ids outside [0, v_bound) raise instead of corrupting memory later; the u side
+        is range-checked by the index build itself (PGLB_ESHAPE)."""
         self = cls()
         self._is_tensor = check_is_tensor(u, v, num_nodes)
+        if v_bound is not None and len(v) > 0:
+            vb = int(v_bound.item()) if isinstance(v_bound, torch.Tensor) else int(v_bound)
+            lo, hi = (int(v.min()), int(v.max()))
+            if lo < 0 or hi >= vb:
+                raise ValueError("edge endpoint %d outside [0, %d)" % (lo if lo < 0 else hi, vb))
         if self._is_tensor:
             n = int(num_nodes.item()) if isinstance(num_nodes, torch.Tensor) else int(num_nodes)
             u = to_tensor(u)

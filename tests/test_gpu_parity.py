@@ -878,3 +878,22 @@ def test_send_ue_recv_wide_rows_gat_shape(pgl, rop):
     y2 = rng.random((e, 5, 1)).astype(np.float32)
     out = g.send_ue_recv(dev(x2), dev(y2), "mul", rop).cpu().numpy()
     assert rel_err(out, O.send_ue_recv(x2, y2, edges[:, 0], edges[:, 1], "mul", rop)) <= RTOL
+
+
+def test_out_of_range_ids_are_rejected_not_dereferenced(pgl):
+    """the device index build range-checks the key column (PGLB_ESHAPE, like the host twin), the other
+    endpoint is checked when the index is built, and a feature matrix with fewer rows than the graph has nodes
+    is refused before any kernel indexes it."""
+    from pgl_b200._lib import PglbError
+    bad_dst = torch.tensor([[0, 1], [1, 7], [2, 3]], dtype=torch.int64, device="cuda")
+    g = pgl.Graph(edges=bad_dst, num_nodes=5)
+    with pytest.raises(PglbError):
+        g.indegree()
+    bad_src = torch.tensor([[0, 1], [9, 2], [2, 3]], dtype=torch.int64, device="cuda")
+    g = pgl.Graph(edges=bad_src, num_nodes=5)
+    with pytest.raises(ValueError):
+        g.send_recv(torch.ones(5, 4, device="cuda"), "sum")
+    ok = pgl.Graph(edges=torch.tensor([[0, 1], [1, 2]], dtype=torch.int64, device="cuda"), num_nodes=5)
+    with pytest.raises(ValueError):
+        ok.send_recv(torch.ones(3, 4, device="cuda"), "sum")
+    assert ok.send_recv(torch.ones(5, 4, device="cuda"), "sum").sum().item() == 8.0
