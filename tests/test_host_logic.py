@@ -152,3 +152,16 @@ def test_bigraph_host_mode():
         g.recv(lambda m: m, {})
     g2 = pgl.BiGraph(edges, src_num_nodes=6, dst_num_nodes=5)
     assert len(g2.indegree()) == 5 and len(g2.outdegree()) == 6
+
+
+def test_pgl_import_alias():
+    """`import pgl` resolves to pgl_b200: same module objects, sub-packages included."""
+    import pgl
+    import pgl_b200
+    import pgl.nn as nn
+    import pgl.nn.functional as GF
+    import pgl.math as pm
+    from pgl.utils import op as uop
+    assert pgl.Graph is pgl_b200.Graph and pgl.BiGraph is pgl_b200.BiGraph
+    assert nn.GCNConv is pgl_b200.nn.GCNConv and GF is pgl_b200.nn.functional
+    assert pm.segment_sum is pgl_b200.math.segment_sum and uop is pgl_b200.utils.op
