@@ -616,16 +616,32 @@ def cpu_and_parity(args, torch, dist, ops, fwd, edges, x, norm, out, step, dev, 
     short = indeg[:n_s] <= 1024
     ex_rows = (gp.view(np.uint32) == prob.out.view(np.uint32)).all(axis=1)
     ps = parity_stats(gp, prob.out)
-    parity["plain_sum"] = {"max_rel_err": ps["max_rel_err"], "bit_exact_rows": int(ex_rows.sum()),
+    # rows of more than 1024 in-edges are cut into tasks whose partial sums are added in task order: a different
+    # (deterministic) fp32 grouping than the oracle's one-by-one loop.  Both are judged against an fp64 sum of the
+    # same row (torch on the device, a checker like the oracle) -- the sequential fp32 loop itself drifts by
+    # ~1e-4 of the result on an 800 000-term row.
+    long_rows = np.flatnonzero(~short)
+    pick = long_rows[np.argsort(indeg[long_rows])[::-1][:64]] if len(long_rows) else long_rows
+    err_gpu = err_orc = 0.0
+    ip_t, cols_t = fwd["indptr"], fwd["cols"]
+    for r in pick.tolist():
+        lo, hi = int(ip_t[r].item()), int(ip_t[r + 1].item())
+        ref64 = x[cols_t[lo:hi]].double().sum(0).cpu().numpy()
+        sc = max(float(np.abs(ref64).max()), 1e-30)
+        err_gpu = max(err_gpu, float(np.abs(gp[r].astype(np.float64) - ref64).max() / sc))
+        err_orc = max(err_orc, float(np.abs(prob.out[r].astype(np.float64) - ref64).max() / sc))
+    parity["plain_sum"] = {"max_rel_err_vs_oracle": ps["max_rel_err"], "bit_exact_rows": int(ex_rows.sum()),
                            "rows_le_1024_edges": int(short.sum()),
                            "all_rows_le_1024_bit_exact": bool(ex_rows[short].all()),
-                           "rows_gt_1024_edges": int((~short).sum())}
-    # the wide-row kernels sum in slot order (bit-exact is part of the bar); the narrow-row kernel (column shards of
-    # <= 64 floats) regroups a row's sum by 32-slot ranges: deterministic, equal to rounding -- reported, not required
+                           "rows_gt_1024_edges": int((~short).sum()), "long_rows_checked_vs_fp64": int(len(pick)),
+                           "long_rows_rel_err_vs_fp64": {"gpu": err_gpu, "oracle_fp32_loop": err_orc}}
+    # the wide-row kernels sum rows of <= 1024 slots in slot order (bit-exact is part of the bar); the narrow-row
+    # kernel (column shards of <= 64 floats) regroups a row's sum by 32-slot ranges: deterministic, equal to rounding
     need_exact = dl > 64
     parity["plain_sum"]["bit_exact_required"] = need_exact
-    parity["pass"] = bool(parity["pass"] and ps["pass"] and
-                          (parity["plain_sum"]["all_rows_le_1024_bit_exact"] or not need_exact))
+    short_ok = parity["plain_sum"]["all_rows_le_1024_bit_exact"] if need_exact else \
+        bool(parity_stats(gp[short], prob.out[short])["max_rel_err"] <= 1e-5)
+    parity["pass"] = bool(parity["pass"] and short_ok and err_gpu <= 3e-5)
     parity["what"] = ("rank %d: GPU output rows dst < %d, columns [%d, %d) vs oracle/oracle_c.c on the same edges and "
                       "features" % (rank, n_s, rank * dl, rank * dl + dl))
     if dist is not None:

@@ -1190,7 +1190,8 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
         if (cv <= 8) return launch_narrow_pk<4>(p, pk, scale_src != nullptr, stream);
         return launch_narrow_pk<2>(p, pk, scale_src != nullptr, stream);
     }
-    if (cv <= 32 && v5_eligible(p, n_src, rk, small_ids)) return launch_v5(p, n_src, stream);
+    if (cv <= 32 && v5_eligible(p, n_src, rk, small_ids))
+        return launch_v5(p, n_src, cols32 != nullptr && cols != nullptr && l2_hints != 0, stream);
     if (cv <= 32 && small_ids) {
         if (y) {  // edge operand: plain int64 ids, no source scale
             return rk ? launch_stream128<1, false, 0, 1>(p, stream) : launch_stream128<0, false, 0, 1>(p, stream);

@@ -55,6 +55,15 @@ __device__ __forceinline__ void tma_gather4(unsigned dst, const CUtensorMap *tm,
         : "memory");
 }
 
+__device__ __forceinline__ void tma_gather4_hint(unsigned dst, const CUtensorMap *tm, int r0, int r1, int r2, int r3,
+                                                 unsigned bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, "
+        "{%2, %3, %4, %5, %6}], [%7], %8;" ::"r"(dst),
+        "l"(tm), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar), "l"(pol)
+        : "memory");
+}
+
 // Geometry: GRP rows per group (one mbarrier / one commit group), NG groups per warp ring, LAG = NG - 1 groups
 // in flight behind the issue point, W warps per CTA (two CTAs per SM).  Per warp: NG*GRP*512 B of rows +
 // 512 B of source norms.
@@ -67,7 +76,7 @@ struct GeoV5 {
     static constexpr int kSmem = W_ * kWarpBytes + 128;  // +128: manual alignment of the dynamic base
 };
 
-template <int ISSUE, bool SCALED, bool D128, int GRP, int NG, int W>
+template <int ISSUE, bool SCALED, bool D128, bool HOT, int GRP, int NG, int W>
 __global__ void __launch_bounds__(W * 32, 2) spmm_v5_kernel(const StreamP p, const __grid_constant__ CUtensorMap tm) {
     typedef GeoV5<GRP, NG, W> G_;
     constexpr int LAG = G_::kLag, GPB = G_::kGpb;
@@ -90,6 +99,10 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_v5_kernel(const StreamP p, con
         __syncwarp();
     }
     if (task >= p.ntasks) return;
+    // HOT: bit 31 of the packed ids marks the most frequently gathered sources (pglb_pack_cols); a quad that holds
+    // one is fetched with the "keep" policy, a quad of cold rows with evict_first so the long tail cannot flush them
+    const uint64_t pol_keep = !HOT ? 0 : (p.hot_mode == 3 ? policy_evict_normal() : policy_evict_last());
+    const uint64_t pol_cold = !HOT ? 0 : (p.hot_mode == 2 ? policy_evict_normal() : policy_evict_first());
     // row pitch in shared memory: the TMA box packs rows of D floats; the LDGSTS ring uses 512-B slots
     // (D128: D == 128, every stride is a compile-time constant)
     const unsigned rp = (ISSUE == 1 && !D128) ? (unsigned)p.D * 4u : 512u;
@@ -165,13 +178,13 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_v5_kernel(const StreamP p, con
         auto load_col = [&](int batch) -> unsigned {
             const int j = batch * 32 + lane;
             if (j >= cnt) return 0u;
-            if (p.cols32) return __ldcs(p.cols32 + a + j) & 0x7fffffffu;
+            if (p.cols32) return HOT ? __ldcs(p.cols32 + a + j) : (__ldcs(p.cols32 + a + j) & 0x7fffffffu);
             return (unsigned)(p.cols ? ld_stream(p.cols + a + j) : (a + j));
         };
         unsigned col_cur = load_col(0);
         unsigned col_nxt = load_col(1);
         if (SCALED) {
-            cp_async4(sring + lane * 4, p.scale_src + col_cur);
+            cp_async4(sring + lane * 4, p.scale_src + (col_cur & 0x7fffffffu));
             if (ISSUE == 1) cp_async_commit();
         }
 
@@ -184,7 +197,7 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_v5_kernel(const StreamP p, con
                     col_cur = col_nxt;
                     col_nxt = load_col(g / GPB + 1);
                     if (SCALED) {
-                        cp_async4(sring + (((g / GPB) & 3) * 32 + lane) * 4, p.scale_src + col_cur);
+                        cp_async4(sring + (((g / GPB) & 3) * 32 + lane) * 4, p.scale_src + (col_cur & 0x7fffffffu));
                         if (ISSUE == 1) cp_async_commit();
                     }
                 }
@@ -198,7 +211,14 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_v5_kernel(const StreamP p, con
                         const int r1 = __shfl_sync(0xffffffffu, col_cur, sub * GRP + q * 4 + 1);
                         const int r2 = __shfl_sync(0xffffffffu, col_cur, sub * GRP + q * 4 + 2);
                         const int r3 = __shfl_sync(0xffffffffu, col_cur, sub * GRP + q * 4 + 3);
-                        if (lane == 0) tma_gather4(ring0 + s * gs + q * qs, &tm, r0, r1, r2, r3, bar0 + s * 8);
+                        if (HOT) {
+                            const uint64_t pol = ((r0 | r1 | r2 | r3) < 0) ? pol_keep : pol_cold;
+                            if (lane == 0)
+                                tma_gather4_hint(ring0 + s * gs + q * qs, &tm, r0 & 0x7fffffff, r1 & 0x7fffffff,
+                                                 r2 & 0x7fffffff, r3 & 0x7fffffff, bar0 + s * 8, pol);
+                        } else if (lane == 0) {
+                            tma_gather4(ring0 + s * gs + q * qs, &tm, r0, r1, r2, r3, bar0 + s * 8);
+                        }
                     }
                 } else {
                     const int valid = cnt - g * GRP;
@@ -206,7 +226,11 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_v5_kernel(const StreamP p, con
 #pragma unroll
                     for (int k = 0; k < GRP; ++k) {
                         const unsigned c = __shfl_sync(0xffffffffu, col_cur, sub * GRP + k);
-                        if (k < valid) cp_async16(gaddr + k * 512, xlane + (size_t)c * row_bytes);
+                        if (k < valid) {
+                            if (HOT) cp_async16_hint(gaddr + k * 512, xlane + (size_t)(c & 0x7fffffffu) * row_bytes,
+                                                     (c >> 31) ? pol_keep : pol_cold);
+                            else cp_async16(gaddr + k * 512, xlane + (size_t)c * row_bytes);
+                        }
                     }
                 }
             }
@@ -347,20 +371,20 @@ static int v5_geo() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("PGLB_V5_GEO");
-        v = e ? atoi(e) : 1;
-        if (v < 0 || v > 2) v = 1;
+        v = e ? atoi(e) : 0;
+        if (v < 0 || v > 2) v = 0;
     }
     return v;
 }
 
-template <int ISSUE, bool SCALED, bool D128, int GRP, int NG, int W>
+template <int ISSUE, bool SCALED, bool D128, bool HOT, int GRP, int NG, int W>
 static int launch_v5_geo(const StreamP &p, const CUtensorMap &tm, cudaStream_t stream) {
     typedef GeoV5<GRP, NG, W> G_;
     static std::atomic<unsigned long long> attr_done{0};
-    PGLB_CUDA(ensure_dyn_smem(spmm_v5_kernel<ISSUE, SCALED, D128, GRP, NG, W>, G_::kSmem, attr_done));
+    PGLB_CUDA(ensure_dyn_smem(spmm_v5_kernel<ISSUE, SCALED, D128, HOT, GRP, NG, W>, G_::kSmem, attr_done));
     const int64_t blocks = (p.ntasks + W - 1) / W;
     PGLB_CHECK_ARG(blocks <= 0x7fffffffLL, PGLB_ESHAPE, "spmm_v5: grid too large");
-    spmm_v5_kernel<ISSUE, SCALED, D128, GRP, NG, W><<<(unsigned)blocks, W * 32, G_::kSmem, stream>>>(p, tm);
+    spmm_v5_kernel<ISSUE, SCALED, D128, HOT, GRP, NG, W><<<(unsigned)blocks, W * 32, G_::kSmem, stream>>>(p, tm);
     PGLB_LAUNCH_CHECK("spmm_v5_kernel");
     const int64_t fblocks = (p.ntasks * 32 + 255) / 256;
     spmm_stream_fixup_kernel<1, 0><<<(unsigned)fblocks, 256, 0, stream>>>(p);
@@ -368,18 +392,20 @@ static int launch_v5_geo(const StreamP &p, const CUtensorMap &tm, cudaStream_t s
     return PGLB_OK;
 }
 
-template <int ISSUE, bool SCALED, bool D128>
-static int launch_v5_d(const StreamP &p, const CUtensorMap &tm, cudaStream_t stream) {
+template <int ISSUE, bool SCALED, bool D128, bool HOT>
+static int launch_v5_h(const StreamP &p, const CUtensorMap &tm, cudaStream_t stream) {
     switch (v5_geo()) {
-        case 1: return launch_v5_geo<ISSUE, SCALED, D128, 8, 4, 6>(p, tm, stream);
-        case 2: return launch_v5_geo<ISSUE, SCALED, D128, 8, 3, 9>(p, tm, stream);
-        default: return launch_v5_geo<ISSUE, SCALED, D128, 4, 4, 13>(p, tm, stream);
+        case 1: return launch_v5_geo<ISSUE, SCALED, D128, HOT, 8, 4, 6>(p, tm, stream);
+        case 2: return launch_v5_geo<ISSUE, SCALED, D128, HOT, 8, 3, 9>(p, tm, stream);
+        default: return launch_v5_geo<ISSUE, SCALED, D128, HOT, 4, 4, 13>(p, tm, stream);
     }
 }
 
 template <int ISSUE, bool SCALED>
-static int launch_v5_issue(const StreamP &p, const CUtensorMap &tm, cudaStream_t stream) {
-    return p.D == 128 ? launch_v5_d<ISSUE, SCALED, true>(p, tm, stream) : launch_v5_d<ISSUE, SCALED, false>(p, tm, stream);
+static int launch_v5_issue(const StreamP &p, const CUtensorMap &tm, bool hot, cudaStream_t stream) {
+    if (p.D == 128)
+        return hot ? launch_v5_h<ISSUE, SCALED, true, true>(p, tm, stream) : launch_v5_h<ISSUE, SCALED, true, false>(p, tm, stream);
+    return launch_v5_h<ISSUE, SCALED, false, false>(p, tm, stream);  // hints only for the 512-byte rows they were tuned on
 }
 
 // true when the v5 kernel can take this call (the caller falls back to spmm_stream128_kernel otherwise)
@@ -393,14 +419,14 @@ static bool v5_eligible(const StreamP &p, int64_t n_src, int rk, bool small_ids)
     return true;
 }
 
-static int launch_v5(const StreamP &p, int64_t n_src, cudaStream_t stream) {
+static int launch_v5(const StreamP &p, int64_t n_src, bool hot, cudaStream_t stream) {
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
     const bool scaled = p.scale_src != nullptr;
     if (v5_mode() == 1) {
         const int rc = make_row_map(&tm, p.x, n_src, p.D, p.ldx);
         if (rc) return rc;
-        return scaled ? launch_v5_issue<1, true>(p, tm, stream) : launch_v5_issue<1, false>(p, tm, stream);
+        return scaled ? launch_v5_issue<1, true>(p, tm, hot, stream) : launch_v5_issue<1, false>(p, tm, hot, stream);
     }
-    return scaled ? launch_v5_issue<0, true>(p, tm, stream) : launch_v5_issue<0, false>(p, tm, stream);
+    return scaled ? launch_v5_issue<0, true>(p, tm, hot, stream) : launch_v5_issue<0, false>(p, tm, hot, stream);
 }
