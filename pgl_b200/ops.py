@@ -48,6 +48,47 @@ def _i64(t):
     return t
 
 
+def f64_through(fn):
+    """float64 in -> float64 out for the public feature ops (the reference's tests/test_conv.py:43-71 runs GCN,
+    GraphSage and GAT in float64).  The kernels are fp32: float64 tensors are rounded to float32 on the way in and
+    the result is widened on the way out (autograd flows through both casts), so a float64 caller gets fp32-accurate
+    values in its own dtype -- within the path's stated 1e-4 relative tolerance, not fp64 accuracy."""
+    import functools
+
+    def is64(t):
+        return isinstance(t, torch.Tensor) and t.dtype == torch.float64
+
+    def down(v):
+        mat = getattr(v, "materialize", None)
+        if mat is not None and getattr(v, "dtype", None) == torch.float64:
+            v = mat()
+        if is64(v):
+            return v.to(torch.float32)
+        if isinstance(v, (list, tuple)):
+            return type(v)(down(a) for a in v)
+        return v
+
+    def any64(v):
+        if is64(v) or (hasattr(v, "materialize") and getattr(v, "dtype", None) == torch.float64):
+            return True
+        return isinstance(v, (list, tuple)) and any(any64(a) for a in v)
+
+    def up(v):
+        if isinstance(v, torch.Tensor) and v.dtype == torch.float32:
+            return v.to(torch.float64)
+        if isinstance(v, tuple):
+            return tuple(up(a) for a in v)
+        return v
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        if not (any(any64(a) for a in args) or any(any64(a) for a in kwargs.values())):
+            return fn(*args, **kwargs)
+        out = fn(*[down(a) for a in args], **{k: down(a) for k, a in kwargs.items()})
+        return up(out)
+    return wrapper
+
+
 def _f32_2d(t):
     """[n, d1, d2, ...] -> contiguous [n, D] float32 view (no copy when already so).  A lazy row
     gather (utils.op.LazyRows) is resolved to its plain tensor first: the wrapper itself carries no
@@ -469,6 +510,7 @@ def _packed_of(csr, x2):
     return fn(n_src, D * 4)
 
 
+@f64_through
 def aggregate_copy(x, fwd, n_dst, reduce_op="sum", bwd=None, scale_src=None, scale_dst=None):
     """send_u_recv on a cached dst-CSR.  fwd/bwd: dicts {indptr, cols, degree, max_degree}."""
     require_cuda(x)
@@ -574,6 +616,7 @@ class _UeAgg(torch.autograd.Function):
         return gx, gy, None, None, None, None, None, None, None
 
 
+@f64_through
 def aggregate_ue(x, y, fwd, n_dst, message_op="add", reduce_op="sum", bwd=None, edges=None):
     """send_ue_recv on a cached dst-CSR: y is in original edge order, read through eid."""
     require_cuda(x, y)
@@ -639,6 +682,7 @@ class _SegmentReduce(torch.autograd.Function):
         return gd, None, None, None, None, None
 
 
+@f64_through
 def segment_reduce(data, segment_ids, pool_type, num_segments=None, indptr=None, cols=None,
                    max_degree=-1):
     """paddle.geometric.segment_* over sorted ids (reference pgl/math.py:36-42).
@@ -712,6 +756,7 @@ class _SendUV(torch.autograd.Function):
         return gx, gy, None, None, None, None, None
 
 
+@f64_through
 def send_uv(x, y, src, dst, message_op="add", src_csr=None, dst_csr=None):
     require_cuda(x, y, src, dst)
     xf = tuple(x.shape[1:]) if x.dim() > 1 else (1,)
@@ -758,6 +803,7 @@ class _GatherRows(torch.autograd.Function):
         return gx, None
 
 
+@f64_through
 def gather_rows(x, index, out=None):
     """paddle.gather(x, index, axis=0).  The kernel is launched on the device of ``index`` /
     ``out``; ``x`` may live on a peer GPU mapped into this process (NVLink P2P pull)."""
@@ -802,6 +848,7 @@ class _ScatterRows(torch.autograd.Function):
         return gi, None, gu
 
 
+@f64_through
 def scatter_rows(init, index, updates):
     """paddle.scatter(init, index, updates, overwrite=True) for unique indices (out-of-place)."""
     require_cuda(init, index, updates)
@@ -843,6 +890,7 @@ class _EdgeSoftmax(torch.autograd.Function):
         return gl, None, None, None
 
 
+@f64_through
 def edge_softmax_csr(indptr, eid, logits, num_edges):
     """Fused per-row softmax; eid=None -> rows are contiguous slots (segment_softmax)."""
     require_cuda(indptr, logits)
@@ -857,6 +905,7 @@ def edge_softmax_csr(indptr, eid, logits, num_edges):
     return out.reshape(shape)
 
 
+@f64_through
 def gat_attention_csr(csr, attn_src, attn_dst, negative_slope=0.2):
     """alpha[slot, h] = softmax over the dst row of leaky_relu(attn_src[src] + attn_dst[dst]) in CSR
     SLOT order (send_uv + LeakyReLU + edge_softmax fused; inference only)."""
@@ -877,6 +926,7 @@ def gat_attention_csr(csr, attn_src, attn_dst, negative_slope=0.2):
     return out
 
 
+@f64_through
 def gat_fused(csr, f, attn_src, attn_dst, negative_slope=0.2):
     """Single-pass GAT aggregation (online softmax in the wide-row kernel).  f [N, H, Dh] with
     H*Dh <= 128 and Dh % 4 == 0; returns [N, H, Dh], or None when the shape is not supported."""
@@ -900,6 +950,7 @@ def gat_fused(csr, f, attn_src, attn_dst, negative_slope=0.2):
     return out.reshape(n_dst, H, Dh)
 
 
+@f64_through
 def aggregate_ue_slots(x, y_slots, fwd, n_dst, message_op="mul", reduce_op="sum"):
     """send_ue_recv whose edge operand is already in CSR slot order (read sequentially)."""
     require_cuda(x, y_slots)
@@ -967,6 +1018,7 @@ class _LinearTC(torch.autograd.Function):
         return gx, gw, gb, None
 
 
+@f64_through
 def linear_tc(x, weight, bias=None, act=None):
     """act(x @ weight + bias) with weight [in, out]; act in (None, "relu")."""
     require_cuda(x, weight)

@@ -246,3 +246,40 @@ def test_fa_conv(pgl):
     out = run(conv, g, dev(x))
     want = OC.fa_conv(edges, n, x, p["gate.weight"], p["gate.bias"])
     assert out.shape == (n, d) and rel_err(out, want) <= RTOL
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_reference_conv_list_in_both_dtypes(pgl, dtype):
+    """reference tests/test_conv.py:43-71: the same conv list on the 5-node graph, under default dtype float32 and
+    float64.  float64 features go through the fp32 kernels (ops.f64_through) and come back as float64; the values
+    must agree with the float32 run to the path's tolerance."""
+    td = getattr(torch, dtype)
+    old = torch.get_default_dtype()
+    rng = np.random.default_rng(5)
+    D = 8
+    edges = [(0, 1), (1, 2), (3, 4)]
+    nfeat = rng.standard_normal((5, D))
+    outs = {}
+    try:
+        for which in (torch.float32, td):
+            torch.set_default_dtype(which)
+            torch.manual_seed(0)
+            convs = [pgl.nn.GCNConv(input_size=D, output_size=D), pgl.nn.GraphSageConv(input_size=D, hidden_size=D),
+                     pgl.nn.GATConv(input_size=D, hidden_size=D), pgl.nn.GCNII(hidden_size=D), pgl.nn.APPNP(),
+                     pgl.nn.SGCConv(input_size=D, output_size=D), pgl.nn.SSGCConv(input_size=D, output_size=D)]
+            g = pgl.Graph(edges=edges, num_nodes=5, node_feat={"nfeat": nfeat.astype(str(which).split(".")[1])})
+            pg = g.tensor()
+            feat = pg.node_feat["nfeat"]
+            assert feat.dtype == which
+            res = []
+            for conv in convs:
+                conv = conv.to("cuda").eval()
+                with torch.no_grad():
+                    out = conv(pg, feat)
+                assert isinstance(out, torch.Tensor) and out.dtype == which, (type(conv).__name__, out.dtype)
+                res.append(out.double().cpu().numpy())
+            outs[which] = res
+    finally:
+        torch.set_default_dtype(old)
+    for a, b in zip(outs[torch.float32], outs[td]):
+        assert np.abs(a - b).max() <= 1e-4 * max(1.0, np.abs(a).max())
