@@ -183,6 +183,12 @@ static int launch(const float *x, int64_t ldx, const float *w, const float *bias
 
 }  // namespace pglb
 
+namespace pglb {
+bool linear_tcgen05_enabled();
+int linear_tcgen05_run(const float *x, int64_t ldx, const float *w, const float *bias, float *out, int64_t ldo,
+                       int64_t M, int act, cudaStream_t stream);
+}  // namespace pglb
+
 extern "C" int pglb_linear_tf32x3_f32(const float *x, int64_t ldx, const float *w, const float *bias,
                                       float *out, int64_t ldo, int64_t M, int64_t K, int64_t N,
                                       int act, void *stream) {
@@ -200,6 +206,9 @@ extern "C" int pglb_linear_tf32x3_f32(const float *x, int64_t ldx, const float *
     PGLB_CHECK_ARG(((uintptr_t)x % 16) == 0 && ((uintptr_t)out % 8) == 0, PGLB_EINVAL,
                    "pglb_linear_tf32x3_f32: x must be 16-byte and out 8-byte aligned");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    // K = N = 128 (the conv layers' hidden size): tcgen05 / TMEM / TMA kernel (csrc/linear_tcgen05.cu)
+    if (K == 128 && N == 128 && linear_tcgen05_enabled())
+        return linear_tcgen05_run(x, ldx, w, bias, out, ldo, M, act, s);
     // PGLB_LINEAR_WARPS = 8 | 16 picks the CTA shape (tuning knob; both are covered by the tests)
     int warps = LT_WARPS_DEFAULT;
     if (const char *e = getenv("PGLB_LINEAR_WARPS")) {
