@@ -616,6 +616,38 @@ class _UeAgg(torch.autograd.Function):
         return gx, gy, None, None, None, None, None, None, None
 
 
+def _ue_with_grad(x2, y2, fwd, bwd, edges, n_dst, mode, hd, message_op, reduce_op):
+    """Differentiable send_ue_recv for every (message_op, reduce_op) of the reference (pgl/graph.py:889-937).
+    add / mul with sum run on the fused kernels (_UeAgg: transpose-SpMM for the node operand, SDDMM / gather for
+    the edge operand).  The rest is composed from those and from pieces that already carry a backward:
+      sub  = add with -y,   div = mul with 1 / y   (autograd differentiates the negation / reciprocal),
+      mean = sum / in-degree,
+      max / min: the [E, D] message is materialised like the reference does (gather_rows(x, src) op y) and reduced
+      by the segment kernel over the dst-CSR slots, whose backward routes the gradient to the selected entries."""
+    if message_op == "sub":
+        return _ue_with_grad(x2, -y2, fwd, bwd, edges, n_dst, mode, hd, "add", reduce_op)
+    if message_op == "div":
+        return _ue_with_grad(x2, 1.0 / y2, fwd, bwd, edges, n_dst, mode, hd, "mul", reduce_op)
+    if reduce_op == "sum":
+        return _UeAgg.apply(x2, y2, fwd, bwd, edges, n_dst, mode, hd, message_op)
+    if reduce_op == "mean":
+        total = _UeAgg.apply(x2, y2, fwd, bwd, edges, n_dst, mode, hd, message_op)
+        deg = (fwd["indptr"][1:] - fwd["indptr"][:-1])[:n_dst].clamp(min=1).to(total.dtype)
+        return total / deg.unsqueeze(1)
+    # max / min
+    D = int(x2.shape[1])
+    xe = gather_rows(x2, edges[:, 0])                                     # [E, D], differentiable
+    if mode == BCAST_FULL:
+        ye = y2
+    elif mode == BCAST_HEAD:
+        ye = y2.reshape(y2.shape[0], D // hd, 1).expand(-1, -1, hd).reshape(y2.shape[0], D)
+    else:
+        ye = y2.reshape(-1, 1).expand(-1, D)
+    msg = xe * ye if message_op == "mul" else xe + ye
+    return segment_reduce(msg, None, reduce_op, indptr=fwd["indptr"][: n_dst + 1], cols=fwd["eid"],
+                          max_degree=fwd.get("max_degree", -1))
+
+
 @f64_through
 def aggregate_ue(x, y, fwd, n_dst, message_op="add", reduce_op="sum", bwd=None, edges=None):
     """send_ue_recv on a cached dst-CSR: y is in original edge order, read through eid."""
@@ -637,11 +669,9 @@ def aggregate_ue(x, y, fwd, n_dst, message_op="add", reduce_op="sum", bwd=None, 
     y2 = _f32_2d(y)
     needs_grad = torch.is_grad_enabled() and (x2.requires_grad or y2.requires_grad)
     if needs_grad:
-        if reduce_op != "sum" or message_op not in ("mul", "add") or bwd is None or edges is None:
-            raise NotImplementedError(
-                "pgl_b200: send_ue_recv is differentiable for message_op in (add, mul) with "
-                "reduce_op sum; got %s / %s" % (message_op, reduce_op))
-        out = _UeAgg.apply(x2, y2, fwd, bwd, edges, n_dst, mode, hd, message_op)
+        if bwd is None or edges is None:
+            raise NotImplementedError("pgl_b200: a differentiable send_ue_recv needs the reverse CSR and the edge list")
+        out = _ue_with_grad(x2, y2, fwd, bwd, edges, n_dst, mode, hd, message_op, reduce_op)
     else:
         out = _spmm_raw(fwd["indptr"], fwd["cols"], x2, n_dst, reduce_op, eid=fwd["eid"], y2=y2,
                         y_bcast=mode, head_dim=hd, msg_op=message_op,

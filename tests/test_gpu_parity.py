@@ -726,9 +726,30 @@ def test_backward_edge_softmax_send_uv_ue(pgl):
         torch.zeros(n, H, Dh, device="cuda").index_add(0, dst, msg).backward(go)
         assert rel_err(x1.grad.cpu().numpy(), x2.grad.cpu().numpy()) <= RTOL, (yshape, mop)
         assert rel_err(y1.grad.cpu().numpy(), y2.grad.cpu().numpy()) <= RTOL, (yshape, mop)
-    with pytest.raises(NotImplementedError):
-        g.send_ue_recv(torch.randn(n, 4, device="cuda", requires_grad=True),
-                       torch.randn(e, 4, device="cuda"), "div", "sum")
+    # every other (message_op, reduce_op) of the reference (pgl/graph.py:889-937) is differentiable too:
+    # sub / div and mean are composed from the fused add / mul + sum path, max / min go through the segment kernel
+    for mop in ("add", "sub", "mul", "div"):
+        for rop in ("sum", "mean", "max", "min"):
+            x1 = torch.randn(n, H, Dh, device="cuda", requires_grad=True)
+            y1 = (torch.rand(e, H, 1, device="cuda") + 0.5).requires_grad_(True)
+            x2, y2 = x1.detach().clone().requires_grad_(True), y1.detach().clone().requires_grad_(True)
+            go = torch.randn(n, H, Dh, device="cuda")
+            out = g.send_ue_recv(x1, y1, mop, rop)
+            out.backward(go)
+            msg = {"add": x2[src] + y2, "sub": x2[src] - y2, "mul": x2[src] * y2, "div": x2[src] / y2}[mop]
+            idx = dst.reshape(-1, 1, 1).expand(-1, H, Dh)
+            if rop in ("sum", "mean"):
+                ref = torch.zeros(n, H, Dh, device="cuda").index_add(0, dst, msg)
+                if rop == "mean":
+                    cnt = torch.bincount(dst, minlength=n).clamp(min=1).reshape(-1, 1, 1)
+                    ref = ref / cnt
+            else:
+                ref = torch.zeros(n, H, Dh, device="cuda").scatter_reduce(
+                    0, idx, msg, "amax" if rop == "max" else "amin", include_self=False)
+            assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= RTOL, (mop, rop)
+            ref.backward(go)
+            assert rel_err(x1.grad.cpu().numpy(), x2.grad.cpu().numpy()) <= RTOL, (mop, rop)
+            assert rel_err(y1.grad.cpu().numpy(), y2.grad.cpu().numpy()) <= RTOL, (mop, rop)
 
 
 def test_backward_max_min(pgl):
