@@ -971,7 +971,7 @@ static int narrow_mode() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("PGLB_NARROW");
-        v = (e && atoi(e) == 0) ? 0 : 1;  // on by default (validated on hardware in round 2); PGLB_NARROW=0 -> generic kernel
+        v = (e && atoi(e) == 1) ? 1 : 0;  // round 1's narrow kernel: validated in round 2, superseded by spmm_narrow2 (opt-in)
     }
     return v;
 }

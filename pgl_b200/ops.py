@@ -464,8 +464,8 @@ class _MaxMinAgg(torch.autograd.Function):
 
 # PGLB_NARROW=1 (experimental): rows of <= 64 floats take the narrow-row streaming kernel, which reads
 # packed column ids like the wide-row kernel
-NARROW_ROWS = os.environ.get("PGLB_NARROW", "1") != "0"      # narrow-row kernels at all (else the generic kernel)
-NARROW2 = os.environ.get("PGLB_NARROW2", "1") != "0"          # spmm_narrow2_kernel (else round 1's spmm_narrow_kernel)
+NARROW2 = os.environ.get("PGLB_NARROW2", "1") != "0"          # spmm_narrow2_kernel for copy-sum / mean over rows of <= 64 floats
+NARROW_ROWS = os.environ.get("PGLB_NARROW") == "1"            # round 1's spmm_narrow_kernel (opt-in, superseded)
 
 
 class NarrowPlan(object):
@@ -500,13 +500,15 @@ def _packed_of(csr, x2):
     wide-row kernels (64 < D <= 128), the narrow plan for D <= 64."""
     fn = csr.get("packed")
     D = int(x2.shape[1])
-    if fn is None or D > 128 or D % 4 or (D <= 64 and not NARROW_ROWS):
+    if fn is None or D > 128 or D % 4 or (D <= 64 and not (NARROW_ROWS or NARROW2)):
         return None
     n_src = int(x2.shape[0])
     if D <= 64 and NARROW2 and csr.get("plan") is not None and 0 < n_src < (1 << 30) and \
             csr["cols"] is not None and int(csr["cols"].shape[0]) > 0:
         plan, nz_row, blk_k = csr["plan"](n_src)
-        return NarrowPlan(plan, nz_row, blk_k, fallback=lambda: fn(n_src, D * 4))
+        return NarrowPlan(plan, nz_row, blk_k, fallback=(lambda: fn(n_src, D * 4)) if NARROW_ROWS else None)
+    if D <= 64 and not NARROW_ROWS:
+        return None
     return fn(n_src, D * 4)
 
 

@@ -1,12 +1,11 @@
-"""GPU tests of the narrow-row streaming kernel (csrc/spmm_stream.cu, spmm_narrow_kernel: rows of <= 64
-floats, 2 / 4 / 8 slots per warp step -- the kernel behind the column-sharded multi-GPU layout).  Validated on
-a B200 in round 2's first GPU call; the narrow path is on by default (PGLB_NARROW=0 turns it off).
+"""GPU tests of the narrow-row kernels: rows of <= 64 floats, the shapes of a column-sharded feature matrix.
+Default path: spmm_narrow2_kernel (csrc/spmm_narrow2.inl: sub-warp-major 32-slot ranges, plan with row-start flags).
+Round 1's spmm_narrow_kernel (csrc/spmm_stream.cu, PGLB_NARROW=1 PGLB_NARROW2=0) is kept as an opt-in and runs the same
+tests in a child process, as does the cut-row variant (PGLB_STREAM_TASK=64: tasks of one chunk, every long row cut) --
+these switches are read once per process by the library.
 
-The task size is read once per process by the library, so the cut-row variant (PGLB_STREAM_TASK=64: rows cut by
-task boundaries everywhere) runs this file again in a child process.
-
-Sum order differs from the sequential oracle (per-sub partial sums + tree), so the bar is the fp32 tolerance,
-not bit equality."""
+Sum order differs from the sequential oracle (ranges of a row are summed separately, then added), so the bar is the
+fp32 tolerance, not bit equality."""
 import os
 
 import numpy as np
@@ -89,14 +88,24 @@ def test_narrow_scaled_and_accumulate(pgl):
     assert rel_err(x1.grad.cpu().numpy(), x2.grad.cpu().numpy()) <= RTOL
 
 
-def test_cut_rows_in_child_process():
-    """The same tests with 64-slot tasks (every long row is cut; partials + fix-up do the work)."""
+def _child(extra_env):
     import subprocess
     import sys
     if os.environ.get("PGLB_NARROW_CHILD") == "1":
         pytest.skip("already the child")
-    env = dict(os.environ, PGLB_STREAM_TASK="64", PGLB_NARROW_CHILD="1")
+    env = dict(os.environ, PGLB_NARROW_CHILD="1", **extra_env)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu",
                         "-p", "no:cacheprovider"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
-                       text=True, timeout=600)
+                       text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:]
+
+
+def test_cut_rows_in_child_process():
+    """The same tests with 64-slot tasks (rounded up to one chunk: every long row is cut; partials + fix-up work)."""
+    _child({"PGLB_STREAM_TASK": "64"})
+
+
+def test_round1_narrow_kernel_in_child_process():
+    """Round 1's narrow kernel stays correct behind its switch (whole rows and cut rows)."""
+    _child({"PGLB_NARROW": "1", "PGLB_NARROW2": "0"})
+    _child({"PGLB_NARROW": "1", "PGLB_NARROW2": "0", "PGLB_STREAM_TASK": "64"})
