@@ -154,13 +154,18 @@ int pglb_pack_cols(const int64_t *cols, int64_t num_edges, int64_t n_src, int32_
  * Row sums are formed in slot order inside 32-slot ranges and the ranges of a row added left to right:
  * deterministic, equal to the sequential loop up to fp32 rounding of the regrouping. */
 int pglb_narrow_plan_ws(int64_t n_dst, size_t *ws_bytes);
-int pglb_narrow_plan(const int64_t *indptr, const int64_t *cols, int64_t n_dst, int64_t n_src, int64_t num_edges,
-                     uint32_t *plan, int32_t *nz_row, int32_t *blk_k, void *ws, size_t ws_bytes, void *stream);
+/* cols_packed (nullable): the uint32 ids of pglb_pack_cols; its bit 31 (L2 residency hint) is carried into the plan */
+int pglb_narrow_plan(const int64_t *indptr, const int64_t *cols, const uint32_t *cols_packed, int64_t n_dst,
+                     int64_t n_src, int64_t num_edges, uint32_t *plan, int32_t *nz_row, int32_t *blk_k, void *ws,
+                     size_t ws_bytes, void *stream);
 int pglb_spmm_narrow_ws(int64_t num_edges, int64_t D, size_t *ws_bytes);
+/* scale_src[n_src] (nullable): gathered per slot.  scale_slot[E] (nullable, wins over scale_src): the same values
+ * already laid out per CSR slot (scale_slot[j] = scale_src[cols[j]], i.e. the edge values of the normalised adjacency),
+ * streamed with the plan instead of gathered.  flags: PGLB_SPMM_L2_HINTS = honour bit 31 of the plan. */
 int pglb_spmm_narrow_f32(const uint32_t *plan, const int32_t *nz_row, const int32_t *blk_k, const int64_t *indptr,
                          const float *x, int64_t ldx, float *out, int64_t ldo, int64_t n_dst, int64_t n_src,
-                         int64_t num_edges, int64_t D, int reduce_op, const float *scale_src, const float *scale_dst,
-                         void *ws, size_t ws_bytes, void *stream);
+                         int64_t num_edges, int64_t D, int reduce_op, const float *scale_src, const float *scale_slot,
+                         const float *scale_dst, int flags, void *ws, size_t ws_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Edge-parallel ops

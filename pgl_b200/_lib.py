@@ -48,10 +48,10 @@ _SIGS = {
     "pglb_spmm_csr_f32": (c_int, [_p, _p, _p, _p, _i64, _p, _i64, c_int, _p, _i64, _i64, _i64, _i64,
                                   _i64, _i64, c_int, c_int, _p, _p, _p, _i64, c_int, _p, c_size_t, _p]),
     "pglb_narrow_plan_ws": (c_int, [_i64, POINTER(c_size_t)]),
-    "pglb_narrow_plan": (c_int, [_p, _p, _i64, _i64, _i64, _p, _p, _p, _p, c_size_t, _p]),
+    "pglb_narrow_plan": (c_int, [_p, _p, _p, _i64, _i64, _i64, _p, _p, _p, _p, c_size_t, _p]),
     "pglb_spmm_narrow_ws": (c_int, [_i64, _i64, POINTER(c_size_t)]),
     "pglb_spmm_narrow_f32": (c_int, [_p, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i64, _i64, _i64, c_int, _p, _p, _p,
-                                     c_size_t, _p]),
+                                     c_int, _p, c_size_t, _p]),
     "pglb_memcpy2d_async": (c_int, [_p, c_size_t, _p, c_size_t, c_size_t, c_size_t, c_int, _p]),
     "pglb_ipc_alloc": (c_int, [c_size_t, POINTER(c_void_p), _p]),
     "pglb_ipc_free": (c_int, [_p]),

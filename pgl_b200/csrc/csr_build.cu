@@ -419,10 +419,12 @@ __global__ void __launch_bounds__(256) segment_indptr_kernel(const int64_t *ids,
 // ---- plan of the narrow-row aggregation (csrc/spmm_narrow2.inl) ----------------------------------------------
 // plan[j] = cols[j] | (slot j starts a row) << 30 ; nz_row[k] = id of the k-th non-empty row (padded with two
 // copies of the last one) ; blk_k[b] = k of the row that owns slot 32 b - 1 (-1 for b = 0).
-__global__ void __launch_bounds__(256) plan_cols_kernel(const int64_t *__restrict__ cols, int64_t E,
+__global__ void __launch_bounds__(256) plan_cols_kernel(const int64_t *__restrict__ cols,
+                                                        const uint32_t *__restrict__ packed, int64_t E,
                                                         uint32_t *__restrict__ plan) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < E) plan[j] = (uint32_t)cols[j];
+    // packed (optional, from pglb_pack_cols): same id with the L2 residency hint in bit 31
+    if (j < E) plan[j] = packed ? (packed[j] & 0xbfffffffu) : (uint32_t)cols[j];
 }
 __global__ void __launch_bounds__(256) plan_rows_kernel(const int64_t *__restrict__ indptr, int64_t N,
                                                         const int64_t *__restrict__ rank,
@@ -568,9 +570,9 @@ extern "C" int pglb_narrow_plan_ws(int64_t N, size_t *ws_bytes) {
     return PGLB_OK;
 }
 
-extern "C" int pglb_narrow_plan(const int64_t *indptr, const int64_t *cols, int64_t N, int64_t n_src, int64_t E,
-                                uint32_t *plan, int32_t *nz_row, int32_t *blk_k, void *ws, size_t ws_bytes,
-                                void *stream_) {
+extern "C" int pglb_narrow_plan(const int64_t *indptr, const int64_t *cols, const uint32_t *cols_packed, int64_t N,
+                                int64_t n_src, int64_t E, uint32_t *plan, int32_t *nz_row, int32_t *blk_k, void *ws,
+                                size_t ws_bytes, void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     PGLB_CHECK_ARG(N > 0 && E > 0, PGLB_EINVAL, "pglb_narrow_plan: needs at least one row and one slot");
     PGLB_CHECK_ARG(N < 0x7fffffffLL && n_src < 0x40000000LL, PGLB_ESHAPE,
@@ -589,7 +591,7 @@ extern "C" int pglb_narrow_plan(const int64_t *indptr, const int64_t *cols, int6
     PGLB_LAUNCH_CHECK("nonempty_flag_kernel");
     const int rc = scan_i64(flag, rank, N, /*inclusive=*/0, tmp, stream);
     if (rc) return rc;
-    plan_cols_kernel<<<(unsigned)((E + 255) / 256), 256, 0, stream>>>(cols, E, plan);
+    plan_cols_kernel<<<(unsigned)((E + 255) / 256), 256, 0, stream>>>(cols, cols_packed, E, plan);
     PGLB_LAUNCH_CHECK("plan_cols_kernel");
     plan_rows_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(indptr, N, rank, plan, nz_row);
     PGLB_LAUNCH_CHECK("plan_rows_kernel");

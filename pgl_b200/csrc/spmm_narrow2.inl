@@ -39,8 +39,10 @@ struct NarrowP {
     int64_t E;
     int D;
     int mean;
-    const float *scale_src;
+    const float *scale_src;  // SC 1: gathered per slot (scale_src[id])
+    const float *sval;       // SC 2: scale_src[id] cached per SLOT (sval[j], streamed like the plan)
     const float *scale_dst;
+    int hot_mode;            // as StreamP: which L2 policies bit 31 of the plan selects
     int64_t T;       // slots per task, a multiple of the chunk size
     int64_t ntasks;
     float *partial;  // [2 * ntasks, dpad]
@@ -50,11 +52,32 @@ struct NarrowP {
 
 constexpr int kNarrowWarps = 8;
 
-template <int LPR, bool SCALED, bool MEAN>
-__global__ void __launch_bounds__(kNarrowWarps * 32) spmm_narrow2_kernel(const NarrowP p) {
+__device__ __forceinline__ float4 ldg128_na(const void *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg128_na_hint(const void *p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+
+// SC: 0 no source scale, 1 gathered (scale_src[id]), 2 cached per slot (sval[j]).  HOT: bit 31 of the plan selects an
+// L2 policy per row (keep the most gathered sources, stream the tail).  U: gathers in flight per lane (8 or 4; fewer
+// registers = more resident warps).
+template <int LPR, int SC, bool MEAN, bool HOT, int U>
+__global__ void __launch_bounds__(kNarrowWarps * 32, (U == 4 ? 3 : 2)) spmm_narrow2_kernel(const NarrowP p) {
     constexpr int EPW = 32 / LPR;      // sub-warps (rows in flight) per warp
     constexpr int CPL = 32 / LPR;      // plan words each lane loads per 32-slot range
-    constexpr int U = 8;               // steps whose gathers are in flight together
+    constexpr bool SCALED = SC != 0;
+    static_assert(U == 8 || U == 4, "8 or 4 gathers in flight per lane");
+    const uint64_t pol_keep = !HOT ? 0 : (p.hot_mode == 3 ? policy_evict_normal() : policy_evict_last());
+    const uint64_t pol_cold = !HOT ? 0 : (p.hot_mode == 2 ? policy_evict_normal() : policy_evict_first());
     static_assert(LPR == 4 || LPR == 8 || LPR == 16, "4, 8 or 16 lanes per row");
     const int lane = threadIdx.x & 31;
     const int64_t task = (int64_t)blockIdx.x * kNarrowWarps + (threadIdx.x >> 5);
@@ -90,10 +113,12 @@ __global__ void __launch_bounds__(kNarrowWarps * 32) spmm_narrow2_kernel(const N
         if (nvalid < 0) nvalid = 0;
         // plan words of my range: lane li holds slots [li * CPL, li * CPL + CPL)
         unsigned creg[CPL];
+        float sreg[SC == 2 ? CPL : 1];
 #pragma unroll
         for (int r = 0; r < CPL; ++r) {
             const int j = li * CPL + r;
             creg[r] = (j < nvalid) ? __ldcs(p.plan + rb + j) : 0u;
+            if (SC == 2) sreg[r] = (j < nvalid) ? __ldcs(p.sval + rb + j) : 0.0f;
         }
         // rows: the one I am in before my first flag, and the next non-empty one
         int k = (nvalid > 0) ? __ldg(p.blk_k + (rb >> 5)) : -1;
@@ -115,13 +140,36 @@ __global__ void __launch_bounds__(kNarrowWarps * 32) spmm_narrow2_kernel(const N
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int j = g * U + u;                        // step inside the range
-                c[u] = __shfl_sync(0xffffffffu, creg[u % CPL], sub * LPR + g * (U / CPL) + u / CPL);
+                // which lane of my sub-warp holds the plan word of step j, and in which register
+                const int wl = (U >= CPL) ? (g * (U / CPL) + u / CPL) : ((g * U + u) / CPL);
+                const int wr = (U >= CPL) ? (u % CPL) : ((g % (CPL / U)) * U + u);
+                unsigned cw;
+                float sw = 0.0f;
+                if (U >= CPL) {
+                    cw = __shfl_sync(0xffffffffu, creg[wr], sub * LPR + wl);
+                    if (SC == 2) sw = __shfl_sync(0xffffffffu, sreg[SC == 2 ? wr : 0], sub * LPR + wl);
+                } else {
+                    // U < CPL: the register index depends on g -- select it without dynamic register indexing
+                    unsigned pick = 0u;
+                    float spick = 0.0f;
+#pragma unroll
+                    for (int q = 0; q < CPL / U; ++q)
+                        if ((g % (CPL / U)) == q) {
+                            pick = creg[q * U + u];
+                            if (SC == 2) spick = sreg[SC == 2 ? q * U + u : 0];
+                        }
+                    cw = __shfl_sync(0xffffffffu, pick, sub * LPR + wl);
+                    if (SC == 2) sw = __shfl_sync(0xffffffffu, spick, sub * LPR + wl);
+                    (void)wr;
+                }
+                c[u] = cw;
                 const unsigned id = c[u] & 0x3fffffffu;
                 v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                s[u] = 0.0f;
+                s[u] = sw;
                 if (j < nvalid) {
-                    v[u] = __ldg(reinterpret_cast<const float4 *>(xlane + (size_t)id * row_bytes));
-                    if (SCALED) s[u] = __ldg(p.scale_src + id);
+                    const void *src = xlane + (size_t)id * row_bytes;
+                    v[u] = HOT ? ldg128_na_hint(src, (c[u] >> 31) ? pol_keep : pol_cold) : ldg128_na(src);
+                    if (SC == 1) s[u] = __ldg(p.scale_src + id);
                 }
             }
 #pragma unroll

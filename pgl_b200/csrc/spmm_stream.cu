@@ -1221,9 +1221,45 @@ static int64_t narrow2_task_size(int64_t E, int64_t D) {
 }
 size_t narrow2_ws_bytes(int64_t E, int64_t D) { return stream_layout(nullptr, E, D, narrow2_task_size(E, D)).bytes; }
 
+static int narrow2_u() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("PGLB_NARROW_U");
+        v = (e && atoi(e) == 4) ? 4 : 8;
+    }
+    return v;
+}
+
+template <int L>
+static void launch_narrow2(const NarrowP &p, int sc, bool hot, int u, unsigned blocks, cudaStream_t stream) {
+#define PGLB_N2K(SC, MN, HT, UU) spmm_narrow2_kernel<L, SC, MN, HT, UU><<<blocks, kNarrowWarps * 32, 0, stream>>>(p)
+    if (p.mean) {  // mean (GraphSAGE): no L2 hints, 8 in flight
+        if (sc == 1) PGLB_N2K(1, true, false, 8);
+        else if (sc == 2) PGLB_N2K(2, true, false, 8);
+        else PGLB_N2K(0, true, false, 8);
+        return;
+    }
+#define PGLB_N2S(SC)                                     \
+    do {                                                 \
+        if (hot) {                                       \
+            if (u == 4) PGLB_N2K(SC, false, true, 4);    \
+            else PGLB_N2K(SC, false, true, 8);           \
+        } else {                                         \
+            if (u == 4) PGLB_N2K(SC, false, false, 4);   \
+            else PGLB_N2K(SC, false, false, 8);          \
+        }                                                \
+    } while (0)
+    if (sc == 1) PGLB_N2S(1);
+    else if (sc == 2) PGLB_N2S(2);
+    else PGLB_N2S(0);
+#undef PGLB_N2S
+#undef PGLB_N2K
+}
+
 int narrow2_run(const uint32_t *plan, const int32_t *nz_row, const int32_t *blk_k, const int64_t *indptr, const float *x,
                 int64_t ldx, float *out, int64_t ldo, int64_t n_dst, int64_t E, int64_t D, int reduce_op,
-                const float *scale_src, const float *scale_dst, void *ws, size_t ws_bytes, cudaStream_t stream) {
+                const float *scale_src, const float *sval, const float *scale_dst, int hot, void *ws, size_t ws_bytes,
+                cudaStream_t stream) {
     const int64_t T = narrow2_task_size(E, D);
     StreamWs w = stream_layout(ws, E, D, T);
     PGLB_CHECK_ARG(ws != nullptr && ws_bytes >= w.bytes, PGLB_EWORKSPACE,
@@ -1241,7 +1277,17 @@ int narrow2_run(const uint32_t *plan, const int32_t *nz_row, const int32_t *blk_
     p.D = (int)D;
     p.mean = reduce_op == PGLB_REDUCE_MEAN;
     p.scale_src = scale_src;
+    p.sval = sval;
     p.scale_dst = scale_dst;
+    {
+        static int mode = 0;
+        if (mode == 0) {
+            const char *e = getenv("PGLB_HOT_MODE");
+            mode = e ? atoi(e) : 1;
+            if (mode < 1 || mode > 3) mode = 1;
+        }
+        p.hot_mode = mode;
+    }
     p.T = T;
     p.ntasks = w.ntasks;
     p.partial = w.partial;
@@ -1269,22 +1315,10 @@ int narrow2_run(const uint32_t *plan, const int32_t *nz_row, const int32_t *blk_
     const int64_t blocks = (p.ntasks + kNarrowWarps - 1) / kNarrowWarps;
     PGLB_CHECK_ARG(blocks <= 0x7fffffffLL, PGLB_ESHAPE, "spmm_narrow2: grid too large");
     const int lpr = narrow2_lpr(D);
-#define PGLB_N2K(L, SC, MN) spmm_narrow2_kernel<L, SC, MN><<<(unsigned)blocks, kNarrowWarps * 32, 0, stream>>>(p)
-#define PGLB_N2(L)                                              \
-    do {                                                        \
-        if (scale_src) {                                        \
-            if (p.mean) PGLB_N2K(L, true, true);                \
-            else PGLB_N2K(L, true, false);                      \
-        } else {                                                \
-            if (p.mean) PGLB_N2K(L, false, true);               \
-            else PGLB_N2K(L, false, false);                     \
-        }                                                       \
-    } while (0)
-    if (lpr == 4) PGLB_N2(4);
-    else if (lpr == 8) PGLB_N2(8);
-    else PGLB_N2(16);
-#undef PGLB_N2K
-#undef PGLB_N2
+    const int sc = sval ? 2 : (scale_src ? 1 : 0);
+    if (lpr == 4) launch_narrow2<4>(p, sc, hot != 0, narrow2_u(), (unsigned)blocks, stream);
+    else if (lpr == 8) launch_narrow2<8>(p, sc, hot != 0, narrow2_u(), (unsigned)blocks, stream);
+    else launch_narrow2<16>(p, sc, hot != 0, narrow2_u(), (unsigned)blocks, stream);
     PGLB_LAUNCH_CHECK("spmm_narrow2_kernel");
     const int64_t fblocks = (p.ntasks * 32 + 255) / 256;
     spmm_stream_fixup_kernel<1, 0><<<(unsigned)fblocks, 256, 0, stream>>>(sp);
@@ -1354,8 +1388,8 @@ extern "C" int pglb_spmm_narrow_ws(int64_t num_edges, int64_t D, size_t *ws_byte
 extern "C" int pglb_spmm_narrow_f32(const uint32_t *plan, const int32_t *nz_row, const int32_t *blk_k,
                                     const int64_t *indptr, const float *x, int64_t ldx, float *out, int64_t ldo,
                                     int64_t n_dst, int64_t n_src, int64_t num_edges, int64_t D, int reduce_op,
-                                    const float *scale_src, const float *scale_dst, void *ws, size_t ws_bytes,
-                                    void *stream_) {
+                                    const float *scale_src, const float *scale_slot, const float *scale_dst, int flags,
+                                    void *ws, size_t ws_bytes, void *stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     PGLB_CHECK_ARG(n_dst > 0 && n_src > 0 && num_edges > 0, PGLB_EINVAL, "pglb_spmm_narrow_f32: empty problem");
     PGLB_CHECK_ARG(D >= 4 && D <= 64 && D % 4 == 0, PGLB_ESHAPE, "pglb_spmm_narrow_f32: D must be 4..64, a multiple of 4");
@@ -1366,6 +1400,6 @@ extern "C" int pglb_spmm_narrow_f32(const uint32_t *plan, const int32_t *nz_row,
                        (ldo % 4) == 0,
                    PGLB_ESHAPE, "pglb_spmm_narrow_f32: x / out rows must be 16-byte aligned");
     PGLB_CHECK_ARG(n_src < 0x40000000LL && ldx * 4 < 0xffffffffLL, PGLB_ESHAPE, "pglb_spmm_narrow_f32: n_src < 2^30 needed");
-    return narrow2_run(plan, nz_row, blk_k, indptr, x, ldx, out, ldo, n_dst, num_edges, D, reduce_op, scale_src, scale_dst,
-                       ws, ws_bytes, stream);
+    return narrow2_run(plan, nz_row, blk_k, indptr, x, ldx, out, ldo, n_dst, num_edges, D, reduce_op, scale_src, scale_slot,
+                       scale_dst, flags & PGLB_SPMM_L2_HINTS, ws, ws_bytes, stream);
 }

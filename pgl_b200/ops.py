@@ -186,11 +186,15 @@ def _spmm_raw(indptr, cols, x2, n_dst, reduce_op, eid=None, y2=None, y_bcast=BCA
             need = ctypes.c_size_t(0)
             check(lib.pglb_spmm_narrow_ws(E, D, ctypes.byref(need)))
             ws = workspace(dev, need.value)
+            sval = None
+            if scale_src is not None and NARROW_SLOT_SCALE and packed.slot_scale is not None:
+                sval = packed.slot_scale(scale_src)     # scale_src[cols[j]] per slot, cached per scale tensor
             with torch.cuda.device(dev):
                 check(lib.pglb_spmm_narrow_f32(_ptr(packed.plan), _ptr(packed.nz_row), _ptr(packed.blk_k),
                                                _ptr(indptr), _ptr(x2), x2.stride(0), _ptr(out), out.stride(0),
                                                n_dst, int(x2.shape[0]), E, D, REDUCE[reduce_op], _ptr(scale_src),
-                                               _ptr(scale_dst), _ptr(ws), ws.numel(), _stream()))
+                                               _ptr(sval), _ptr(scale_dst), 2 if packed.hints else 0, _ptr(ws),
+                                               ws.numel(), _stream()))
             return out
         packed = packed.fallback() if packed.fallback is not None else None
     need = ctypes.c_size_t(0)
@@ -468,21 +472,29 @@ NARROW2 = os.environ.get("PGLB_NARROW2", "1") != "0"          # spmm_narrow2_ker
 NARROW_ROWS = os.environ.get("PGLB_NARROW") == "1"            # round 1's spmm_narrow_kernel (opt-in, superseded)
 
 
+NARROW_HOT_BYTES = int(float(os.environ.get("PGLB_NARROW_HOT_MB", "64")) * (1 << 20))   # L2 residency budget, narrow rows
+NARROW_SLOT_SCALE = os.environ.get("PGLB_NARROW_SLOT_SCALE", "1") != "0"                 # stream cached per-slot norms
+
+
 class NarrowPlan(object):
-    """What pglb_spmm_narrow_f32 streams instead of cols / indptr (see include/pglb.h); `fallback()` gives the
-    packed column ids for calls the narrow kernel does not take (max / min, accumulate, unaligned views)."""
-    __slots__ = ("plan", "nz_row", "blk_k", "fallback")
+    """What pglb_spmm_narrow_f32 streams instead of cols / indptr (see include/pglb.h).  `hints`: bit 31 of the plan
+    carries an L2 residency hint.  `slot_scale(scale_src)`: the source scale laid out per CSR slot (cached per scale
+    tensor by the EdgeIndex).  `fallback()` gives the packed column ids for calls the narrow kernel does not take."""
+    __slots__ = ("plan", "nz_row", "blk_k", "hints", "slot_scale", "fallback")
 
-    def __init__(self, plan, nz_row, blk_k, fallback=None):
-        self.plan, self.nz_row, self.blk_k, self.fallback = plan, nz_row, blk_k, fallback
+    def __init__(self, plan, nz_row, blk_k, hints=False, slot_scale=None, fallback=None):
+        self.plan, self.nz_row, self.blk_k, self.hints = plan, nz_row, blk_k, bool(hints)
+        self.slot_scale, self.fallback = slot_scale, fallback
 
 
-def narrow_plan(indptr, cols, n_src):
-    """Build the plan of a dst-CSR once (cached by the EdgeIndex)."""
+def narrow_plan(indptr, cols, n_src, row_bytes=64):
+    """Build the plan of a dst-CSR once (cached by the EdgeIndex).  Returns (plan, nz_row, blk_k, hints)."""
     require_cuda(indptr, cols)
     dev = indptr.device
     n_dst = int(indptr.shape[0]) - 1
     E = int(cols.shape[0])
+    pk = pack_cols(cols, n_src, row_bytes, NARROW_HOT_BYTES) if NARROW_HOT_BYTES > 0 else None
+    hints = bool(pk is not None and pk[1])
     plan = torch.empty(E, dtype=torch.int32, device=dev)
     nz_row = torch.empty(n_dst + 2, dtype=torch.int32, device=dev)
     blk_k = torch.empty((E + 31) // 32, dtype=torch.int32, device=dev)
@@ -490,9 +502,9 @@ def narrow_plan(indptr, cols, n_src):
     check(lib.pglb_narrow_plan_ws(n_dst, ctypes.byref(need)))
     ws = workspace(dev, need.value)
     with torch.cuda.device(dev):
-        check(lib.pglb_narrow_plan(_ptr(indptr), _ptr(cols), n_dst, int(n_src), E, _ptr(plan), _ptr(nz_row),
-                                   _ptr(blk_k), _ptr(ws), ws.numel(), _stream()))
-    return plan, nz_row, blk_k
+        check(lib.pglb_narrow_plan(_ptr(indptr), _ptr(cols), _ptr(pk[0]) if hints else None, n_dst, int(n_src), E,
+                                   _ptr(plan), _ptr(nz_row), _ptr(blk_k), _ptr(ws), ws.numel(), _stream()))
+    return plan, nz_row, blk_k, hints
 
 
 def _packed_of(csr, x2):
@@ -505,8 +517,9 @@ def _packed_of(csr, x2):
     n_src = int(x2.shape[0])
     if D <= 64 and NARROW2 and csr.get("plan") is not None and 0 < n_src < (1 << 30) and \
             csr["cols"] is not None and int(csr["cols"].shape[0]) > 0:
-        plan, nz_row, blk_k = csr["plan"](n_src)
-        return NarrowPlan(plan, nz_row, blk_k, fallback=(lambda: fn(n_src, D * 4)) if NARROW_ROWS else None)
+        plan, nz_row, blk_k, hints = csr["plan"](n_src, D * 4)
+        return NarrowPlan(plan, nz_row, blk_k, hints, slot_scale=csr.get("slot_scale"),
+                          fallback=(lambda: fn(n_src, D * 4)) if NARROW_ROWS else None)
     if D <= 64 and not NARROW_ROWS:
         return None
     return fn(n_src, D * 4)

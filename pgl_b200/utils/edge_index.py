@@ -124,18 +124,33 @@ class EdgeIndex(object):
             cache[key] = ops.pack_cols(self._sorted_v, n_src, row_bytes)
         return cache[key]
 
-    def narrow_plan(self, n_src):
-        """Cached plan of the narrow-row kernel (see ops.narrow_plan): depends on the index only."""
+    def narrow_plan(self, n_src, row_bytes=64):
+        """Cached plan of the narrow-row kernel (see ops.narrow_plan).  The row flags depend on the index only; the
+        L2 residency hints on how many rows of this width fit the budget, hence the key."""
         cache = self.__dict__.setdefault("_plan_cache", {})
-        if "plan" not in cache:
-            cache["plan"] = ops.narrow_plan(self._indptr, self._sorted_v, n_src)
-        return cache["plan"]
+        key = int(row_bytes) if ops.NARROW_HOT_BYTES > 0 else 0
+        if key not in cache:
+            cache[key] = ops.narrow_plan(self._indptr, self._sorted_v, n_src, row_bytes)
+        return cache[key]
+
+    def slot_scale(self, scale_src):
+        """scale_src[cols[j]] for every CSR slot j -- the edge values of the normalised adjacency -- cached per scale
+        tensor (identity + in-place version counter), so the narrow-row kernel streams 4 bytes per slot instead of
+        gathering a 32-byte sector per edge."""
+        cache = self.__dict__.setdefault("_slot_scale_cache", {})
+        key = (scale_src.data_ptr(), int(scale_src._version), int(scale_src.numel()))
+        hit = cache.get("key") == key
+        if not hit:
+            cache["key"] = key
+            cache["val"] = scale_src.reshape(-1)[self._sorted_v].contiguous()
+            cache["ref"] = scale_src          # keeps the storage alive, so the data_ptr cannot be recycled
+        return cache["val"]
 
     def csr(self):
         """dict consumed by pgl_b200.ops: rows keyed by u, columns = v, eid per slot."""
         return {"indptr": self._indptr, "cols": self._sorted_v, "eid": self._sorted_eid,
                 "degree": self._degree, "max_degree": self.max_degree, "packed": self.packed_cols,
-                "plan": self.narrow_plan}
+                "plan": self.narrow_plan, "slot_scale": self.slot_scale}
 
     def view_v(self, u=None):
         """reference pgl/utils/edge_index.py:103-114 (numpy mode only)."""

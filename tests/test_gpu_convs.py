@@ -264,6 +264,7 @@ def test_reference_conv_list_in_both_dtypes(pgl, dtype):
         for which in (torch.float32, td):
             torch.set_default_dtype(which)
             torch.manual_seed(0)
+            prev = outs.get("convs")
             convs = [pgl.nn.GCNConv(input_size=D, output_size=D), pgl.nn.GraphSageConv(input_size=D, hidden_size=D),
                      pgl.nn.GATConv(input_size=D, hidden_size=D), pgl.nn.GCNII(hidden_size=D), pgl.nn.APPNP(),
                      pgl.nn.SGCConv(input_size=D, output_size=D), pgl.nn.SSGCConv(input_size=D, output_size=D)]
@@ -272,6 +273,10 @@ def test_reference_conv_list_in_both_dtypes(pgl, dtype):
             feat = pg.node_feat["nfeat"]
             assert feat.dtype == which
             res = []
+            if prev is not None:   # same parameters as the float32 run (random init differs per dtype)
+                for c_new, c_old in zip(convs, prev):
+                    c_new.load_state_dict({k: v.to(which) for k, v in c_old.state_dict().items()})
+            outs["convs"] = convs
             for conv in convs:
                 conv = conv.to("cuda").eval()
                 with torch.no_grad():
