@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-full-layer", action="store_true")
     ap.add_argument("--shard", default=os.environ.get("PGLB_SHARD", "cols"), choices=["cols", "rows"])
+    ap.add_argument("--grid", default=os.environ.get("PGLB_GRID", ""),
+                    help="N > 1, --shard cols: RrxRc = row groups x column groups (default: 2 column groups)")
     ap.add_argument("--partition", default="block", choices=["block", "metis"])
     ap.add_argument("--halo", default=os.environ.get("PGLB_HALO_MODE", "p2p"), choices=["nccl", "p2p"])
     ap.add_argument("--overlap", action="store_true")
@@ -217,13 +219,15 @@ class CpuGcn(object):
     ``run(threads)``: threads == 1 -> the sequential COO loop (Paddle's CPU send_u_recv contract);
     threads > 1 -> the row-threaded CSR twin (bit-identical results, oracle/oracle_c.c)."""
 
-    def __init__(self, lib, src_np, dst_np, n, dim, frac, threads):
+    def __init__(self, lib, src_np, dst_np, n, dim, frac, threads, n_rows=None):
+        """n: rows of the feature matrix (sources); n_rows: destination rows of this edge list (default n)."""
         self.lib, self.n, self.dim, self.frac = lib, int(n), int(dim), float(frac)
+        self.n_rows = int(n if n_rows is None else n_rows)
         self.e_total = int(len(src_np))
         if frac >= 1.0:
-            self.n_s, self.src, self.dst = self.n, src_np, dst_np
+            self.n_s, self.src, self.dst = self.n_rows, src_np, dst_np
         else:
-            self.n_s = max(1, int(n * frac))
+            self.n_s = max(1, int(self.n_rows * frac))
             m = dst_np < self.n_s
             self.src = np.ascontiguousarray(src_np[m])
             self.dst = np.ascontiguousarray(dst_np[m])
@@ -241,12 +245,12 @@ class CpuGcn(object):
             assert rc == 0
             del su, se, deg
         self.sample = ("rows dst < %d (%.2f%% of the graph's rows with all their in-edges: %d of %d edges), "
-                       "full %d-row feature matrix" % (self.n_s, 100.0 * self.n_s / self.n, self.e_s,
+                       "full %d-row feature matrix" % (self.n_s, 100.0 * self.n_s / self.n_rows, self.e_s,
                                                        self.e_total, self.n))
         self.xs = None
         self.out = None
 
-    def run(self, x_np, norm_np, threads, scaled=True):
+    def run(self, x_np, norm_np, threads, scaled=True, norm_dst_np=None):
         """One pass.  Returns (seconds charged, detail).  The source scaling touches all N rows whatever
         the sample is; its time is charged in proportion to the sample (frac), everything else in full."""
         lib, d = self.lib, self.dim
@@ -272,10 +276,11 @@ class CpuGcn(object):
         t_scale_out = 0.0
         if scaled:
             t0 = time.perf_counter()
-            lib.orc_scale_rows_f32(_ptr(self.out), _ptr(norm_np), _i64(self.n_s), _i64(d), _ptr(self.out),
+            nd = norm_np if norm_dst_np is None else norm_dst_np   # norm of the destination rows (local numbering)
+            lib.orc_scale_rows_f32(_ptr(self.out), _ptr(nd), _i64(self.n_s), _i64(d), _ptr(self.out),
                                    int(threads))
             t_scale_out = time.perf_counter() - t0
-        charged = t_scale_in * min(1.0, self.n_s / self.n) + t_agg + t_scale_out
+        charged = t_scale_in * min(1.0, self.n_s / self.n_rows) + t_agg + t_scale_out
         return charged, {"scale_src_s_full_matrix": t_scale_in, "aggregate_s": t_agg, "scale_dst_s": t_scale_out,
                          "charged_s": charged, "threads": int(threads), "sample_edges": self.e_s,
                          "sample_rows": self.n_s, "edges_per_s": self.e_s / charged if charged > 0 else None}
@@ -444,22 +449,57 @@ def main_ours(args):
         raise SystemExit("bench.py: parity check against the oracle FAILED: %r" % (result["parity"],))
 
 
+def parse_grid(args, world):
+    """(row groups, column groups).  Default for N > 1: two column groups (256-byte rows, the narrowest the memory
+    system still serves at >= 0.7 of the HBM roofline -- DESIGN.md section 5) x N/2 destination-row groups."""
+    if world == 1:
+        return 1, 1
+    if args.grid:
+        rr, rc = (int(v) for v in args.grid.lower().split("x"))
+    else:
+        rc = 2
+        rr = world // rc
+    assert rr * rc == world, "--grid RrxRc must multiply to the number of ranks"
+    return rr, rc
+
+
+def block_bounds(n, parts, i):
+    base, rem = divmod(n, parts)
+    lo = i * base + min(i, rem)
+    return lo, lo + base + (1 if i < rem else 0)
+
+
 def bench_gcn(args, torch, dist, pgl, ops, GF, dev, world, rank):
-    """cfg5 at 1 GPU, and column-sharded at N GPUs (rank r owns columns [r*D/N, (r+1)*D/N) of every row)."""
+    """cfg5 at 1 GPU; at N GPUs on an Rr x Rc grid: rank (r, c) owns destination rows block r and feature columns
+    block c of every source row (column blocks are replicated across the Rr row groups, as the reference's
+    DistGPUGraph replicates whole features).  No exchange inside the aggregation for any grid."""
     n, e, d = args.nodes, args.edges, args.dim
-    assert d % world == 0 and (d // world) % 4 == 0, "feature width must split into 16-byte column slices"
-    dl = d // world
-    c0 = rank * dl
+    rr, rc = parse_grid(args, world)
+    r, c = rank // rc, rank % rc
+    assert d % rc == 0 and (d // rc) % 4 == 0, "feature width must split into 16-byte column slices"
+    dl = d // rc
+    c0 = c * dl
+    lo, hi = block_bounds(n, rr, r)
+    n_loc = hi - lo
     hbm_gbs, peak_src = peaks()
 
     t0 = time.perf_counter()
-    edges = gen_edges(torch, n, e, args.exponent, args.seed, dev)   # same seed: every rank holds the whole graph
+    edges = gen_edges(torch, n, e, args.exponent, args.seed, dev)   # same seed: every rank sees the whole graph
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t0
-    g = pgl.Graph(edges=edges, num_nodes=n)
+    indeg = torch.bincount(edges[:, 1], minlength=n)
+    norm = ops.degree_norm(indeg).reshape(-1)                        # global clip(in-degree, 1)^-0.5
+    if rr > 1:
+        m = (edges[:, 1] >= lo) & (edges[:, 1] < hi)
+        edges_loc = torch.stack([edges[m, 0], edges[m, 1] - lo], 1)  # my rows' in-edges, destinations renumbered
+        del m
+    else:
+        edges_loc = edges
+    e_loc = int(edges_loc.shape[0])
+    g = pgl.Graph(edges=edges_loc, num_nodes=n)
     s0, s1 = _ev(torch), _ev(torch)
     g._fwd_csr()                     # first call pays one-off costs (module load, workspace growth): not the build time
-    g2 = pgl.Graph(edges=edges, num_nodes=n)
+    g2 = pgl.Graph(edges=edges_loc, num_nodes=n)
     torch.cuda.synchronize()
     s0.record()
     g2._fwd_csr()                    # device CSR build, steady state
@@ -467,18 +507,18 @@ def bench_gcn(args, torch, dist, pgl, ops, GF, dev, world, rank):
     torch.cuda.synchronize()
     t_csr_ms = s0.elapsed_time(s1)
     del g2
-    fwd = g._fwd_csr()
-    norm = GF.degree_norm(g).reshape(-1)
+    fwd = g._csr_for_rows(n_loc)     # dst-CSR truncated to my rows (the rows behind them have no in-edges)
+    norm_dst = norm[lo:hi].contiguous()
     x_full = gen_features(torch, n, d, args.seed + 1, dev)
-    x = x_full if world == 1 else x_full[:, c0:c0 + dl].contiguous()
+    x = x_full if rc == 1 else x_full[:, c0:c0 + dl].contiguous()
     del x_full
     torch.cuda.empty_cache()
-    out = torch.empty(n, dl, device=dev)
+    out = torch.empty(n_loc, dl, device=dev)
     packed = ops._packed_of(fwd, x)  # cached per graph: packed column ids (wide rows) or the narrow-row plan
 
     def step():
-        return ops._spmm_raw(fwd["indptr"], fwd["cols"], x, n, "sum", scale_src=norm,
-                             scale_dst=norm, max_degree=fwd["max_degree"], out=out, packed=packed)
+        return ops._spmm_raw(fwd["indptr"], fwd["cols"], x, n_loc, "sum", scale_src=norm,
+                             scale_dst=norm_dst, max_degree=fwd["max_degree"], out=out, packed=packed)
 
     warm = max(args.warmup, 3)
     for _ in range(warm):
@@ -491,34 +531,42 @@ def bench_gcn(args, torch, dist, pgl, ops, GF, dev, world, rank):
     launches = ops.launch_count() - l0
     clocks = sampler.stop()
     kern_ms = float(np.mean(per))
+    b_alg = algorithmic_bytes(n_loc, e_loc, dl)    # this rank's kernel: its edges, its rows, its columns
+    achieved = b_alg / (kern_ms * 1e-3) / 1e9
+    per_rank = None
     if dist is not None:
-        t = torch.tensor([total_ms, kern_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, kern_ms = float(t[0].item()), float(t[1].item())
+        total_ms = float(t[0].item())
         lt = torch.tensor([launches], device=dev, dtype=torch.int64)
         dist.all_reduce(lt)
         launches = int(lt.item())
+        mine = {"rank": rank, "grid_pos": [r, c], "rows": n_loc, "edges": e_loc, "cols": dl, "kernel_ms": kern_ms,
+                "algorithmic_bytes": b_alg, "achieved_GBs": achieved}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+        slow = min(per_rank, key=lambda q: q["achieved_GBs"])   # the roofline line quotes the least efficient rank
+        kern_ms, b_alg, achieved = slow["kernel_ms"], slow["algorithmic_bytes"], slow["achieved_GBs"]
     ms_step = total_ms / args.steps
     value = e / (ms_step * 1e-3)
-    b_alg = algorithmic_bytes(n, e, dl)            # per GPU: every edge, D/N columns
-    achieved = b_alg / (kern_ms * 1e-3) / 1e9
 
     # ---- parity against the oracle, in this run ---------------------------------------------
     cpu = None
     parity = None
     if not args.no_cpu:
         try:
-            cpu, parity = cpu_and_parity(args, torch, dist, ops, fwd, edges, x, norm, out, step, dev, world, rank,
-                                         n, d, dl)
+            cpu, parity = cpu_and_parity(args, torch, dist, ops, fwd, edges_loc, indeg, x, norm, norm_dst, out, step,
+                                         dev, world, rank, n, n_loc, lo, c0, dl)
         except Exception as ex:
             cpu = {"value": None, "unit": "edges/s", "cores": 1, "kind": "port", "sample": "failed: %r" % (ex,)}
             parity = {"pass": None, "error": repr(ex)[:300]}
 
-    # ---- full GCN layer through the public API -----------------------------------------------
+    # ---- full GCN layer ------------------------------------------------------------------------
     full = None
     if not args.no_full_layer:
         try:
-            full = full_layer(args, torch, dist, pgl, g, x, norm, dev, world, rank, n, e, d, dl)
+            full = full_layer(args, torch, dist, pgl, ops, g, step, x, norm, dev, world, rank, rr, rc, r, c, n, n_loc,
+                              e, d, dl)
         except Exception as ex:
             full = {"value": None, "error": repr(ex)[:300]}
 
@@ -526,13 +574,17 @@ def bench_gcn(args, torch, dist, pgl, ops, GF, dev, world, rank):
     e2e = None
     if not args.no_e2e:
         try:
-            e2e = e2e_host(args, torch, dist, g, x, norm, dev, world, n, e, dl)
+            e2e = e2e_host(args, torch, dist, ops, g, fwd, x, norm, norm_dst, dev, world, n, n_loc, e, dl)
         except Exception as ex:
             e2e = {"value": None, "unit": "edges/s", "error": repr(ex)[:300]}
 
-    par = "single GPU" if world == 1 else \
-        ("%d-way COLUMN shard: every GPU holds the whole CSR and %d of the %d feature columns of all rows; the "
-         "aggregation needs no exchange (full_layer adds the [N, D/R] -> [N/R, D] all-to-all)" % (world, dl, d))
+    if world == 1:
+        par = "single GPU"
+    else:
+        par = ("%d x %d grid: %d destination-row groups x %d feature-column groups; a rank holds the in-edges of its "
+               "%d rows and %d of the %d feature columns of ALL source rows (column blocks replicated across the row "
+               "groups); the aggregation needs no exchange (full_layer adds the re-shard to whole rows)" %
+               (rr, rc, rr, rc, n_loc, dl, d))
     return {
         "metric": "edges/sec per GCN layer (128-d feat)", "value": value, "unit": "edges/s",
         "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_step,
@@ -540,44 +592,51 @@ def bench_gcn(args, torch, dist, pgl, ops, GF, dev, world, rank):
         "data": "synthetic",
         "config": {"workload": workload_name(args),
                    "l2": "inputs (%.2f GB of feature rows per GPU) larger than L2" % (n * dl * 4 / 1e9),
-                   "parallelism": par, "csr_build_ms": t_csr_ms, "graph_gen_s": t_gen,
+                   "parallelism": par, "grid": [rr, rc], "csr_build_ms": t_csr_ms, "graph_gen_s": t_gen,
                    "max_in_degree": int(fwd["max_degree"]), "index_dtype": "int64",
                    "packed_cols": packed is not None, "narrow_plan": isinstance(packed, ops.NarrowPlan),
-                   "l2_hints": bool(packed is not None and not isinstance(packed, ops.NarrowPlan) and packed[1]),
-                   "stream_v5": os.environ.get("PGLB_STREAM_V5", "default")},
+                   "l2_hints": bool(packed.hints if isinstance(packed, ops.NarrowPlan) else (packed is not None and packed[1])),
+                   "stream_v5": os.environ.get("PGLB_STREAM_V5", "default"), "per_rank": per_rank},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
                      "frac": achieved / hbm_gbs,
                      "traffic": read_traffic("spmm_csr_kernel_bytes_per_launch" if world == 1 else
-                                             "colshard%d_bytes_per_launch" % world),
+                                             "grid%dx%d_bytes_per_launch" % (rr, rc)),
                      "peak_source": peak_src, "frac_of_nominal_8000GBs": achieved / 8000.0,
                      "algorithmic_bytes": b_alg,
-                     "note": "per GPU: E*(4*Dl+8) + N*4*Dl + (N+1)*8 + 2*N*4 with Dl = %d columns, over the slowest "
-                             "rank's mean kernel time (CUDA events around each step on the launching stream)" % dl,
-                     "kernel": kernel_name(), "kernel_ms_mean": kern_ms,
+                     "note": "the least efficient rank's kernel: E_r*(4*Dl+8) + N_r*4*Dl + (N_r+1)*8 + 2*N_r*4 bytes "
+                             "(its edges, its rows, Dl = %d columns) over its mean kernel time (CUDA events around each "
+                             "step on the launching stream)" % dl,
+                     "kernel": kernel_name() if dl > 64 else "spmm_narrow2_kernel (+ empty_rows, fix-up kernels)",
+                     "kernel_ms_mean": kern_ms,
                      "kernel_ms_p10": per[len(per) // 10], "kernel_ms_p90": per[(len(per) * 9) // 10]},
         "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "full_layer": full,
     }
 
 
-def cpu_and_parity(args, torch, dist, ops, fwd, edges, x, norm, out, step, dev, world, rank, n, d, dl):
-    """Rank 0: the oracle's 1-thread COO pass on a bounded row sample (cpu_baseline).  Every rank: its
-    columns of the GPU output on the sample rows against the oracle's output for the same inputs --
+def cpu_and_parity(args, torch, dist, ops, fwd, edges_loc, gdeg, x, norm, norm_dst, out, step, dev, world, rank, n,
+                   n_loc, lo, c0, dl):
+    """Rank 0: the oracle's 1-thread COO pass on a bounded row sample (cpu_baseline).  Every rank: its block of the
+    GPU output (its rows, its columns) on a row sample against the oracle's output for the same inputs --
     (a) the GCN-normalised aggregation (tolerance 1e-4: the kernel fuses x*norm into an FMA),
-    (b) the plain sum, which must be BIT-EXACT on every row of <= 1024 in-edges (same summation order)."""
+    (b) the plain sum: BIT-EXACT on every row of <= 1024 in-edges for the wide-row kernels (same summation order),
+        rounding-level for the narrow-row kernel, and long rows judged against an fp64 sum."""
     lib = _load_oracle_c()
-    src_np = np.ascontiguousarray(edges[:, 0].cpu().numpy())
-    dst_np = np.ascontiguousarray(edges[:, 1].cpu().numpy())
+    src_np = np.ascontiguousarray(edges_loc[:, 0].cpu().numpy())
+    dst_np = np.ascontiguousarray(edges_loc[:, 1].cpu().numpy())
     x_np = x.cpu().numpy()
     norm_np = norm.cpu().numpy()
-    indeg = fwd["degree"].cpu().numpy()
-    norm_ref = cpu_norm(indeg)
+    indeg = fwd["degree"][:n_loc].cpu().numpy()
+    # the oracle's norm needs the GLOBAL in-degree of every source (the ranks' norm vector came from the same counts)
+    gdeg_np = gdeg.cpu().numpy()
+    norm_ref = cpu_norm(gdeg_np)
+    norm_dst_ref = np.ascontiguousarray(norm_ref[lo:lo + n_loc])
     threads = host_threads()
     cpu = None
     if rank == 0:
         # calibrate: about 12 s of single-thread work
-        probe = CpuGcn(lib, src_np, dst_np, n, dl, 0.005, 1)
-        t1, _ = probe.run(x_np, norm_ref, 1)
+        probe = CpuGcn(lib, src_np, dst_np, n, dl, 0.005, 1, n_rows=n_loc)
+        t1, _ = probe.run(x_np, norm_ref, 1, norm_dst_np=norm_dst_ref)
         frac = min(1.0, max(0.005, 0.005 * 12.0 / max(t1, 1e-3)))
         del probe
     else:
@@ -587,28 +646,28 @@ def cpu_and_parity(args, torch, dist, ops, fwd, edges, x, norm, out, step, dev, 
         dist.broadcast(ft, 0)
         frac = float(ft.item())
     if rank != 0:
-        frac = min(frac, 0.02)  # the other ranks only check: a 2 % row sample of their columns
-    prob = CpuGcn(lib, src_np, dst_np, n, dl, frac, threads)
+        frac = min(frac, 0.02)  # the other ranks only check: a 2 % sample of their rows
+    prob = CpuGcn(lib, src_np, dst_np, n, dl, frac, threads, n_rows=n_loc)
     n_s = prob.n_s
     if rank == 0:
-        t1, det1 = prob.run(x_np, norm_ref, 1)
+        t1, det1 = prob.run(x_np, norm_ref, 1, norm_dst_np=norm_dst_ref)
         cpu = {"value": prob.e_s / t1, "unit": "edges/s", "cores": 1, "kind": "port", "sample": prob.sample,
                "detail": {"coo_1thread": det1}}
         want = prob.out.copy()
         if threads > 1:
-            tt, dett = prob.run(x_np, norm_ref, threads)
+            tt, dett = prob.run(x_np, norm_ref, threads, norm_dst_np=norm_dst_ref)
             cpu["detail"]["csr_threads"] = dict(dett, identical_to_coo=bool(np.array_equal(want, prob.out)))
     else:
-        prob.run(x_np, norm_ref, threads)
+        prob.run(x_np, norm_ref, threads, norm_dst_np=norm_dst_ref)
         want = prob.out.copy()
     step()
     torch.cuda.synchronize()
     got = out[:n_s].cpu().numpy()
     parity = parity_stats(got, want)
     parity["norm_bit_exact"] = bool(np.array_equal(norm_np, norm_ref))
-    # (b) plain sum, bit-exact where the order is the sequential one
+    # (b) plain sum
     prob.run(x_np, norm_ref, threads, scaled=False)
-    plain = ops._spmm_raw(fwd["indptr"], fwd["cols"], x, n, "sum", max_degree=fwd["max_degree"],
+    plain = ops._spmm_raw(fwd["indptr"], fwd["cols"], x, n_loc, "sum", max_degree=fwd["max_degree"],
                           packed=ops._packed_of(fwd, x))
     torch.cuda.synchronize()
     gp = plain[:n_s].cpu().numpy()
@@ -624,42 +683,42 @@ def cpu_and_parity(args, torch, dist, ops, fwd, edges, x, norm, out, step, dev, 
     pick = long_rows[np.argsort(indeg[long_rows])[::-1][:64]] if len(long_rows) else long_rows
     err_gpu = err_orc = 0.0
     ip_t, cols_t = fwd["indptr"], fwd["cols"]
-    for r in pick.tolist():
-        lo, hi = int(ip_t[r].item()), int(ip_t[r + 1].item())
-        ref64 = x[cols_t[lo:hi]].double().sum(0).cpu().numpy()
+    for rrow in pick.tolist():
+        a0, a1 = int(ip_t[rrow].item()), int(ip_t[rrow + 1].item())
+        ref64 = x[cols_t[a0:a1]].double().sum(0).cpu().numpy()
         sc = max(float(np.abs(ref64).max()), 1e-30)
-        err_gpu = max(err_gpu, float(np.abs(gp[r].astype(np.float64) - ref64).max() / sc))
-        err_orc = max(err_orc, float(np.abs(prob.out[r].astype(np.float64) - ref64).max() / sc))
+        err_gpu = max(err_gpu, float(np.abs(gp[rrow].astype(np.float64) - ref64).max() / sc))
+        err_orc = max(err_orc, float(np.abs(prob.out[rrow].astype(np.float64) - ref64).max() / sc))
     parity["plain_sum"] = {"max_rel_err_vs_oracle": ps["max_rel_err"], "bit_exact_rows": int(ex_rows.sum()),
                            "rows_le_1024_edges": int(short.sum()),
                            "all_rows_le_1024_bit_exact": bool(ex_rows[short].all()),
                            "rows_gt_1024_edges": int((~short).sum()), "long_rows_checked_vs_fp64": int(len(pick)),
                            "long_rows_rel_err_vs_fp64": {"gpu": err_gpu, "oracle_fp32_loop": err_orc}}
     # the wide-row kernels sum rows of <= 1024 slots in slot order (bit-exact is part of the bar); the narrow-row
-    # kernel (column shards of <= 64 floats) regroups a row's sum by 32-slot ranges: deterministic, equal to rounding
+    # kernel (column blocks of <= 64 floats) regroups a row's sum by 32-slot ranges: deterministic, equal to rounding
     need_exact = dl > 64
     parity["plain_sum"]["bit_exact_required"] = need_exact
     short_ok = parity["plain_sum"]["all_rows_le_1024_bit_exact"] if need_exact else \
         bool(parity_stats(gp[short], prob.out[short])["max_rel_err"] <= 1e-5)
     parity["pass"] = bool(parity["pass"] and short_ok and err_gpu <= 3e-5)
-    parity["what"] = ("rank %d: GPU output rows dst < %d, columns [%d, %d) vs oracle/oracle_c.c on the same edges and "
-                      "features" % (rank, n_s, rank * dl, rank * dl + dl))
+    parity["what"] = ("rank %d: GPU output rows [%d, %d) of the graph, columns [%d, %d) vs oracle/oracle_c.c on the same "
+                      "edges and features" % (rank, lo, lo + n_s, c0, c0 + dl))
     if dist is not None:
         allp = [None] * world
         dist.all_gather_object(allp, parity)
-        parity = {"pass": all(bool(p["pass"]) for p in allp), "tol": PARITY_TOL,
-                  "max_rel_err": max(p["max_rel_err"] for p in allp),
-                  "rows": sum(p["rows"] for p in allp),
-                  "bit_exact_rows": sum(p["plain_sum"]["bit_exact_rows"] for p in allp), "per_rank": allp}
+        parity = {"pass": all(bool(q["pass"]) for q in allp), "tol": PARITY_TOL,
+                  "max_rel_err": max(q["max_rel_err"] for q in allp),
+                  "rows": sum(q["rows"] for q in allp),
+                  "bit_exact_rows": sum(q["plain_sum"]["bit_exact_rows"] for q in allp), "per_rank": allp}
     else:
         parity["bit_exact_rows_gcn"] = parity["bit_exact_rows"]
         parity["bit_exact_rows"] = parity["plain_sum"]["bit_exact_rows"]
     return cpu, parity
 
 
-def full_layer(args, torch, dist, pgl, g, x, norm, dev, world, rank, n, e, d, dl):
-    """GCNConv(128,128,relu).forward.  N = 1: the public layer.  N > 1: aggregate my columns (no exchange) ->
-    all-to-all [N, D/R] -> [N/R, D] -> dense transform + bias + ReLU of my row block."""
+def full_layer(args, torch, dist, pgl, ops, g, step, x, norm, dev, world, rank, rr, rc, r, c, n, n_loc, e, d, dl):
+    """GCNConv(128,128,relu).forward.  N = 1: the public layer.  N > 1: aggregate my block (no exchange) ->
+    all-to-all inside my row group ([rows, D/Rc] -> [rows/Rc, D]) -> dense transform + bias + ReLU of those rows."""
     kf = max(3, args.steps // 4)
     if world == 1:
         conv = pgl.nn.GCNConv(d, d, activation="relu").to(dev)
@@ -677,17 +736,17 @@ def full_layer(args, torch, dist, pgl, g, x, norm, dev, world, rank, n, e, d, dl
         del y
         return {"value": e / (full_ms * 1e-3), "unit": "edges/s", "ms": full_ms,
                 "what": "GCNConv(128,128,relu).forward: aggregation + dense transform with bias + ReLU in its "
-                        "epilogue (3xTF32 tensor cores, csrc/linear_tc.cu)"}
+                        "epilogue (3xTF32 on tcgen05 tensor cores, csrc/linear_tcgen05.cu)"}
     from pgl_b200.distributed import ColumnShardedGraph
-    from pgl_b200 import ops
-    cs = ColumnShardedGraph(g, d, world, rank)
+    groups = [dist.new_group(list(range(q * rc, (q + 1) * rc))) for q in range(rr)]   # every rank creates every group
+    cs = ColumnShardedGraph(None, d, rc, c, group=groups[r])
     torch.manual_seed(7)
     w = (torch.randn(d, d, device=dev) / d ** 0.5).contiguous()
     b = torch.zeros(d, device=dev)
 
     def layer():
-        agg = cs.gcn_aggregate(x, norm)
-        rows = cs.to_rows(agg)
+        agg = step()
+        rows = cs.to_rows(agg) if rc > 1 else agg
         return ops.linear_tc(rows, w, b, "relu")
 
     with torch.no_grad():
@@ -706,41 +765,46 @@ def full_layer(args, torch, dist, pgl, g, x, norm, dev, world, rank, n, e, d, dl
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         full_ms = float(t.item())
     return {"value": e / (full_ms * 1e-3), "unit": "edges/s", "ms": full_ms,
-            "what": "column-sharded GCN layer: aggregate my %d columns (no exchange) -> NCCL all-to-all to whole rows "
-                    "of my row block -> dense transform + bias + ReLU; output row-sharded [N/%d, %d]" % (dl, world, d)}
+            "what": "GCN layer on the %d x %d grid: aggregate my block (no exchange) -> NCCL all-to-all inside my row group "
+                    "to whole rows -> dense transform + bias + ReLU; output row-sharded [N/%d, %d].  Re-replicating the "
+                    "output columns for a NEXT layer (all-gather across the %d row groups) is not included" %
+                    (rr, rc, world, d, rr)}
 
 
-def e2e_host(args, torch, dist, g, x, norm, dev, world, n, e, dl):
-    """Public host-buffer API: this rank's [N, Dl] feature columns start in pinned host memory and its result ends
-    in pinned host memory, every step.  `value` pipelines successive steps (HostAggregator.submit / wait: the
+def e2e_host(args, torch, dist, ops, g, fwd, x, norm, norm_dst, dev, world, n, n_loc, e, dl):
+    """Public host-buffer API: this rank's [N, Dl] feature columns start in pinned host memory and its [N_r, Dl] result
+    ends in pinned host memory, every step.  `value` pipelines successive steps (HostAggregator.submit / wait: the
     upload of step i+1 overlaps the kernel and download of step i over full-duplex PCIe); `single_call_ms` is one
-    blocking Graph.send_recv_host call."""
+    blocking call."""
     x_host = torch.empty((n, dl), dtype=torch.float32, pin_memory=True)
     x_host.copy_(x)
-    out_host = torch.empty((n, dl), dtype=torch.float32, pin_memory=True)
+    out_host = torch.empty((n_loc, dl), dtype=torch.float32, pin_memory=True)
     chunks = int(os.environ.get("PGLB_E2E_CHUNKS", "2"))
+    blocking = ops.HostAggregator(fwd, n, n_loc, dl, dev, chunks, depth=1) if n_loc != n else g.host_aggregator(n, dl, chunks, 1)
     for _ in range(2):
-        g.send_recv_host(x_host, out_host, "sum", scale_src=norm, scale_dst=norm, chunks=chunks)
+        blocking(x_host, out_host, "sum", scale_src=norm, scale_dst=norm_dst)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
-    g.send_recv_host(x_host, out_host, "sum", scale_src=norm, scale_dst=norm, chunks=chunks)
+    blocking(x_host, out_host, "sum", scale_src=norm, scale_dst=norm_dst)
     single_ms = (time.perf_counter() - t0) * 1e3
-    ref = g._send_u_recv(x, "sum", None, scale_src=norm, scale_dst=norm)
+    ref = ops._spmm_raw(fwd["indptr"], fwd["cols"], x, n_loc, "sum", scale_src=norm, scale_dst=norm_dst,
+                        max_degree=fwd["max_degree"], packed=ops._packed_of(fwd, x))
     diff_single = float((out_host.to(dev) - ref).abs().max().item())
+    del blocking
 
-    agg = g.host_aggregator(n, dl, chunks=int(os.environ.get("PGLB_E2E_PIPE_CHUNKS", "1")), depth=2)
+    agg = ops.HostAggregator(fwd, n, n_loc, dl, dev, int(os.environ.get("PGLB_E2E_PIPE_CHUNKS", "1")), depth=2)
     out_host.zero_()
     for _ in range(2):
-        agg.wait(agg.submit(x_host, out_host, "sum", scale_src=norm, scale_dst=norm))
+        agg.wait(agg.submit(x_host, out_host, "sum", scale_src=norm, scale_dst=norm_dst))
     ke = max(3, min(args.steps, 8))
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     q0, q1 = _ev(torch), _ev(torch)
     q0.record()
-    tickets = [agg.submit(x_host, out_host, "sum", scale_src=norm, scale_dst=norm) for _ in range(ke)]
+    tickets = [agg.submit(x_host, out_host, "sum", scale_src=norm, scale_dst=norm_dst) for _ in range(ke)]
     for t in tickets:
         torch.cuda.current_stream().wait_event(t)
     q1.record()
@@ -750,20 +814,22 @@ def e2e_host(args, torch, dist, g, x, norm, dev, world, n, e, dl):
     e2e_ms = q0.elapsed_time(q1) / ke
     diff_pipe = float((out_host.to(dev) - ref).abs().max().item())
     del ref
-    nbytes = n * dl * 4
+    h2d, d2h = n * dl * 4, n_loc * dl * 4
     if dist is not None:
         t = torch.tensor([e2e_ms, single_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms, single_ms = float(t[0].item()), float(t[1].item())
-        nbytes *= world
+        bt = torch.tensor([h2d, d2h], device=dev, dtype=torch.float64)
+        dist.all_reduce(bt)
+        h2d, d2h = int(bt[0].item()), int(bt[1].item())
     return {"value": e / (e2e_ms * 1e-3), "unit": "edges/s",
-            "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "ms_per_step": e2e_ms, "steps": ke, "single_call_ms": single_ms,
             "max_abs_diff_vs_resident": max(diff_single, diff_pipe),
-            "api": "Graph.host_aggregator(...).submit/wait (sum + degree norms) on a resident graph: features from "
-                   "pinned host memory, result back in pinned host memory, every step; successive steps are "
-                   "double-buffered so the upload of step i+1 overlaps kernel + download of step i.  "
-                   "single_call_ms = one blocking Graph.send_recv_host call (%d column chunks)" % chunks}
+            "api": "ops.HostAggregator.submit/wait (sum + degree norms) on a resident graph shard: this rank's feature "
+                   "columns from pinned host memory, its output block back in pinned host memory, every step; successive "
+                   "steps are double-buffered so the upload of step i+1 overlaps kernel + download of step i.  "
+                   "single_call_ms = one blocking call (%d column chunks)" % chunks}
 
 
 # ------------------------------------------------------------------------------------------

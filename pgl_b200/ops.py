@@ -379,7 +379,7 @@ def gather_rows_ptr(src_ptr, ld, index, out):
     return out
 
 
-HOT_L2_BYTES = int(float(os.environ.get("PGLB_HOT_MB", "32")) * (1 << 20))
+HOT_L2_BYTES = int(float(os.environ.get("PGLB_HOT_MB", "64")) * (1 << 20))
 
 
 def pack_cols(cols, n_src, row_bytes, budget_bytes=None):
