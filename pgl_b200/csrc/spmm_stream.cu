@@ -1004,6 +1004,7 @@ static int launch_narrow_pk(const StreamP &p, int pk, bool scaled, cudaStream_t 
 }
 
 #include "spmm_v5.inl"
+#include "spmm_gat5.inl"
 #include "spmm_narrow2.inl"
 
 struct StreamWs {
@@ -1372,6 +1373,7 @@ int gat_fused_run(const int64_t *indptr, const int64_t *cols, const float *f, in
         const int rc = launch_empty_rows(p, stream);
         if (rc) return rc;
     }
+    if (gat5_eligible(p, f, ldf, attn_src, H, n_src)) return launch_gat5(p, attn_src, H, n_src, stream);
     return launch_stream128<0, false, 0, 2>(p, stream);
 }
 
