@@ -450,23 +450,35 @@ def main_ours(args):
 
 
 def parse_grid(args, world):
-    """(row groups, column groups).  Default for N > 1: two column groups (256-byte rows, the narrowest the memory
-    system still serves at >= 0.7 of the HBM roofline -- DESIGN.md section 5) x N/2 destination-row groups."""
+    """(row groups Rr, column groups Rc).  Default for N > 1: Rr = N, Rc = 1 -- every GPU aggregates the in-edges of its
+    block of destination rows from a local replica of the source features (the reference's DistGPUGraph layout,
+    pgl/graph.py:1490: edges by destination, features replicated -- minus its all-reduce of the [N, D] output, which a
+    row-sharded output does not need).  `--grid 1xN` is the pure column shard, anything between a mix; DESIGN.md
+    section 5 has the measured table and what each layout costs a full layer."""
     if world == 1:
         return 1, 1
     if args.grid:
         rr, rc = (int(v) for v in args.grid.lower().split("x"))
     else:
-        rc = 2
-        rr = world // rc
+        rr, rc = world, 1
     assert rr * rc == world, "--grid RrxRc must multiply to the number of ranks"
     return rr, rc
 
 
-def block_bounds(n, parts, i):
-    base, rem = divmod(n, parts)
-    lo = i * base + min(i, rem)
-    return lo, lo + base + (1 if i < rem else 0)
+def balanced_row_bounds(torch, indeg, parts):
+    """Row-block boundaries with (nearly) equal numbers of in-edges per block: a block of rows costs what its edges
+    cost, and a power-law graph's hubs make equal ROW counts unequal work."""
+    n = int(indeg.shape[0])
+    if parts == 1:
+        return [0, n]
+    csum = torch.cumsum(indeg, 0)
+    total = int(csum[-1].item())
+    targets = torch.tensor([total * k // parts for k in range(1, parts)], device=indeg.device, dtype=csum.dtype)
+    cuts = torch.searchsorted(csum, targets).tolist()
+    b = [0] + [min(max(int(c) + 1, 1), n) for c in cuts] + [n]
+    for i in range(1, len(b)):           # strictly increasing even on degenerate inputs
+        b[i] = max(b[i], b[i - 1])
+    return b
 
 
 def bench_gcn(args, torch, dist, pgl, ops, GF, dev, world, rank):
@@ -479,8 +491,6 @@ def bench_gcn(args, torch, dist, pgl, ops, GF, dev, world, rank):
     assert d % rc == 0 and (d // rc) % 4 == 0, "feature width must split into 16-byte column slices"
     dl = d // rc
     c0 = c * dl
-    lo, hi = block_bounds(n, rr, r)
-    n_loc = hi - lo
     hbm_gbs, peak_src = peaks()
 
     t0 = time.perf_counter()
@@ -488,6 +498,9 @@ def bench_gcn(args, torch, dist, pgl, ops, GF, dev, world, rank):
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t0
     indeg = torch.bincount(edges[:, 1], minlength=n)
+    bounds = balanced_row_bounds(torch, indeg, rr)                   # identical on every rank
+    lo, hi = bounds[r], bounds[r + 1]
+    n_loc = hi - lo
     norm = ops.degree_norm(indeg).reshape(-1)                        # global clip(in-degree, 1)^-0.5
     if rr > 1:
         m = (edges[:, 1] >= lo) & (edges[:, 1] < hi)
@@ -574,7 +587,8 @@ def bench_gcn(args, torch, dist, pgl, ops, GF, dev, world, rank):
     e2e = None
     if not args.no_e2e:
         try:
-            e2e = e2e_host(args, torch, dist, ops, g, fwd, x, norm, norm_dst, dev, world, n, n_loc, e, dl)
+            e2e = e2e_host(args, torch, dist, ops, g, fwd, x, norm, norm_dst, dev, world, rank, rr, rc, r, c, bounds, n,
+                           n_loc, e, dl)
         except Exception as ex:
             e2e = {"value": None, "unit": "edges/s", "error": repr(ex)[:300]}
 
@@ -592,7 +606,7 @@ def bench_gcn(args, torch, dist, pgl, ops, GF, dev, world, rank):
         "data": "synthetic",
         "config": {"workload": workload_name(args),
                    "l2": "inputs (%.2f GB of feature rows per GPU) larger than L2" % (n * dl * 4 / 1e9),
-                   "parallelism": par, "grid": [rr, rc], "csr_build_ms": t_csr_ms, "graph_gen_s": t_gen,
+                   "parallelism": par, "grid": [rr, rc], "row_blocks": "balanced by in-edge count", "csr_build_ms": t_csr_ms, "graph_gen_s": t_gen,
                    "max_in_degree": int(fwd["max_degree"]), "index_dtype": "int64",
                    "packed_cols": packed is not None, "narrow_plan": isinstance(packed, ops.NarrowPlan),
                    "l2_hints": bool(packed.hints if isinstance(packed, ops.NarrowPlan) else (packed is not None and packed[1])),
@@ -771,40 +785,70 @@ def full_layer(args, torch, dist, pgl, ops, g, step, x, norm, dev, world, rank, 
                     (rr, rc, world, d, rr)}
 
 
-def e2e_host(args, torch, dist, ops, g, fwd, x, norm, norm_dst, dev, world, n, n_loc, e, dl):
-    """Public host-buffer API: this rank's [N, Dl] feature columns start in pinned host memory and its [N_r, Dl] result
-    ends in pinned host memory, every step.  `value` pipelines successive steps (HostAggregator.submit / wait: the
-    upload of step i+1 overlaps the kernel and download of step i over full-duplex PCIe); `single_call_ms` is one
-    blocking call."""
-    x_host = torch.empty((n, dl), dtype=torch.float32, pin_memory=True)
-    x_host.copy_(x)
-    out_host = torch.empty((n_loc, dl), dtype=torch.float32, pin_memory=True)
-    chunks = int(os.environ.get("PGLB_E2E_CHUNKS", "2"))
-    blocking = ops.HostAggregator(fwd, n, n_loc, dl, dev, chunks, depth=1) if n_loc != n else g.host_aggregator(n, dl, chunks, 1)
-    for _ in range(2):
+def e2e_host(args, torch, dist, ops, g, fwd, x, norm, norm_dst, dev, world, rank, rr, rc, r, c, bounds, n, n_loc, e, dl):
+    """Features start in pinned host memory and the result ends in pinned host memory, every step.
+    N = 1: the public host-buffer API (HostAggregator.submit / wait pipelines successive steps; `single_call_ms` is
+    one blocking Graph.send_recv_host).  N > 1: every rank uploads only ITS row block of its column block (the
+    feature matrix crosses PCIe once in total, not once per row group), the row groups complete each other's
+    replicas by an NCCL all-gather over NVLink (distributed.GridHostAggregator), then kernel and download."""
+    if world == 1:
+        x_host = torch.empty((n, dl), dtype=torch.float32, pin_memory=True)
+        x_host.copy_(x)
+        out_host = torch.empty((n_loc, dl), dtype=torch.float32, pin_memory=True)
+        chunks = int(os.environ.get("PGLB_E2E_CHUNKS", "2"))
+        blocking = g.host_aggregator(n, dl, chunks, 1)
+        for _ in range(2):
+            blocking(x_host, out_host, "sum", scale_src=norm, scale_dst=norm_dst)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         blocking(x_host, out_host, "sum", scale_src=norm, scale_dst=norm_dst)
-    torch.cuda.synchronize()
-    if dist is not None:
+        single_ms = (time.perf_counter() - t0) * 1e3
+        ref = ops._spmm_raw(fwd["indptr"], fwd["cols"], x, n_loc, "sum", scale_src=norm, scale_dst=norm_dst,
+                            max_degree=fwd["max_degree"], packed=ops._packed_of(fwd, x))
+        diff_single = float((out_host.to(dev) - ref).abs().max().item())
+        del blocking
+        agg = ops.HostAggregator(fwd, n, n_loc, dl, dev, int(os.environ.get("PGLB_E2E_PIPE_CHUNKS", "1")), depth=2)
+        submit = lambda: agg.submit(x_host, out_host, "sum", scale_src=norm, scale_dst=norm_dst)   # noqa: E731
+        h2d, d2h = n * dl * 4, n_loc * dl * 4
+        api = ("Graph.host_aggregator(...).submit / wait (sum + degree norms) on a resident graph: features from pinned "
+               "host memory, result back in pinned host memory, every step; successive steps are double-buffered so the "
+               "upload of step i+1 overlaps kernel + download of step i.  single_call_ms = one blocking "
+               "Graph.send_recv_host call (%d column chunks)" % chunks)
+    else:
+        from pgl_b200.distributed import GridHostAggregator
+        ub = [block_bounds(n, rr, q)[0] for q in range(rr)] + [n]    # upload split of the source rows: even blocks
+        lo, hi = ub[r], ub[r + 1]
+        x_host = torch.empty((hi - lo, dl), dtype=torch.float32, pin_memory=True)
+        x_host.copy_(x[lo:hi])
+        out_host = torch.empty((n_loc, dl), dtype=torch.float32, pin_memory=True)
+        agg = GridHostAggregator(fwd, n, n_loc, dl, dev, rr, rc, r, c, ub)
+        t0 = None
+        for _ in range(2):
+            agg.wait(agg.submit(x_host, out_host, "sum", scale_src=norm, scale_dst=norm_dst))
+        torch.cuda.synchronize()
         dist.barrier()
-    t0 = time.perf_counter()
-    blocking(x_host, out_host, "sum", scale_src=norm, scale_dst=norm_dst)
-    single_ms = (time.perf_counter() - t0) * 1e3
-    ref = ops._spmm_raw(fwd["indptr"], fwd["cols"], x, n_loc, "sum", scale_src=norm, scale_dst=norm_dst,
-                        max_degree=fwd["max_degree"], packed=ops._packed_of(fwd, x))
-    diff_single = float((out_host.to(dev) - ref).abs().max().item())
-    del blocking
-
-    agg = ops.HostAggregator(fwd, n, n_loc, dl, dev, int(os.environ.get("PGLB_E2E_PIPE_CHUNKS", "1")), depth=2)
+        t0 = time.perf_counter()
+        agg.wait(agg.submit(x_host, out_host, "sum", scale_src=norm, scale_dst=norm_dst))
+        single_ms = (time.perf_counter() - t0) * 1e3
+        ref = ops._spmm_raw(fwd["indptr"], fwd["cols"], x, n_loc, "sum", scale_src=norm, scale_dst=norm_dst,
+                            max_degree=fwd["max_degree"], packed=ops._packed_of(fwd, x))
+        diff_single = float((out_host.to(dev) - ref).abs().max().item())
+        submit = lambda: agg.submit(x_host, out_host, "sum", scale_src=norm, scale_dst=norm_dst)   # noqa: E731
+        h2d, d2h = (hi - lo) * dl * 4, n_loc * dl * 4
+        api = ("distributed.GridHostAggregator.submit / wait: every rank uploads its row block of its column block from "
+               "pinned host memory (the matrix crosses PCIe once in total), NCCL all-gather over NVLink completes the "
+               "source replica of each row group, aggregation, output block back to pinned host memory; two buffer sets, "
+               "upload of step i+1 overlaps step i.  single_call_ms = one step alone")
     out_host.zero_()
     for _ in range(2):
-        agg.wait(agg.submit(x_host, out_host, "sum", scale_src=norm, scale_dst=norm_dst))
+        agg.wait(submit())
     ke = max(3, min(args.steps, 8))
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     q0, q1 = _ev(torch), _ev(torch)
     q0.record()
-    tickets = [agg.submit(x_host, out_host, "sum", scale_src=norm, scale_dst=norm_dst) for _ in range(ke)]
+    tickets = [submit() for _ in range(ke)]
     for t in tickets:
         torch.cuda.current_stream().wait_event(t)
     q1.record()
@@ -814,7 +858,6 @@ def e2e_host(args, torch, dist, ops, g, fwd, x, norm, norm_dst, dev, world, n, n
     e2e_ms = q0.elapsed_time(q1) / ke
     diff_pipe = float((out_host.to(dev) - ref).abs().max().item())
     del ref
-    h2d, d2h = n * dl * 4, n_loc * dl * 4
     if dist is not None:
         t = torch.tensor([e2e_ms, single_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -825,11 +868,7 @@ def e2e_host(args, torch, dist, ops, g, fwd, x, norm, norm_dst, dev, world, n, n
     return {"value": e / (e2e_ms * 1e-3), "unit": "edges/s",
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "ms_per_step": e2e_ms, "steps": ke, "single_call_ms": single_ms,
-            "max_abs_diff_vs_resident": max(diff_single, diff_pipe),
-            "api": "ops.HostAggregator.submit/wait (sum + degree norms) on a resident graph shard: this rank's feature "
-                   "columns from pinned host memory, its output block back in pinned host memory, every step; successive "
-                   "steps are double-buffered so the upload of step i+1 overlaps kernel + download of step i.  "
-                   "single_call_ms = one blocking call (%d column chunks)" % chunks}
+            "max_abs_diff_vs_resident": max(diff_single, diff_pipe), "api": api}
 
 
 # ------------------------------------------------------------------------------------------

@@ -17,3 +17,4 @@ aggregation it fetches just the distinct remote source rows it needs ("halo").
 from .halo import HaloPlan, block_offsets, relabel_by_partition  # noqa: F401
 from .colshard import ColumnShardedGraph  # noqa: F401
 from .sharded import ShardedGraph  # noqa: F401
+from .grid import GridHostAggregator, column_group  # noqa: F401

@@ -165,3 +165,22 @@ def test_pgl_import_alias():
     assert pgl.Graph is pgl_b200.Graph and pgl.BiGraph is pgl_b200.BiGraph
     assert nn.GCNConv is pgl_b200.nn.GCNConv and GF is pgl_b200.nn.functional
     assert pm.segment_sum is pgl_b200.math.segment_sum and uop is pgl_b200.utils.op
+
+
+def test_bench_balanced_row_bounds():
+    """bench.py's destination-row blocks: contiguous, cover every row, nearly equal in-edge counts (hubs included)."""
+    import torch
+    import bench
+    rng = np.random.default_rng(9)
+    indeg = rng.integers(0, 5, 10000)
+    indeg[[17, 4000, 9000]] = [30000, 20000, 10000]       # hubs
+    t = torch.from_numpy(indeg.astype(np.int64))
+    for parts in (1, 2, 4, 8):
+        b = bench.balanced_row_bounds(torch, t, parts)
+        assert b[0] == 0 and b[-1] == 10000 and len(b) == parts + 1 and all(b[i] <= b[i + 1] for i in range(parts))
+        per = [int(indeg[b[i]:b[i + 1]].sum()) for i in range(parts)]
+        assert sum(per) == int(indeg.sum())
+        assert max(per) <= indeg.sum() / parts + indeg.max()   # within one (hub) row of the ideal share
+    assert bench.block_bounds(10, 4, 0) == (0, 3) and bench.block_bounds(10, 4, 3) == (8, 10)
+    assert bench.parse_grid(type("A", (), {"grid": ""})(), 8) == (8, 1)
+    assert bench.parse_grid(type("A", (), {"grid": "2x4"})(), 8) == (2, 4)
