@@ -465,6 +465,13 @@ def parse_grid(args, world):
     return rr, rc
 
 
+def block_bounds(n, parts, i):
+    """[lo, hi) of the i-th of `parts` nearly equal contiguous blocks of range(n)."""
+    base, rem = divmod(n, parts)
+    lo = i * base + min(i, rem)
+    return lo, lo + base + (1 if i < rem else 0)
+
+
 def balanced_row_bounds(torch, indeg, parts):
     """Row-block boundaries with (nearly) equal numbers of in-edges per block: a block of rows costs what its edges
     cost, and a power-law graph's hubs make equal ROW counts unequal work."""
