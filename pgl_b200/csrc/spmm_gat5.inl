@@ -28,6 +28,7 @@ struct Gat5P {
     unsigned fq;      // stride of a quad of feature rows (aligned to 128)
     unsigned aq;      // stride of a quad of attention rows (aligned to 128)
     unsigned ap;      // attention row pitch (H * 4)
+    int64_t task_mul; // task id = (linear warp id * task_mul) % ntasks, gcd(task_mul, ntasks) == 1
 };
 
 template <int GRP, int NG, int W>
@@ -40,7 +41,11 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_gat5_kernel(const Gat5P gp, co
     __shared__ __align__(8) unsigned long long bars[W * NG];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const int64_t task = (int64_t)blockIdx.x * W + wib;
+    // RMAT-like graphs put the hub rows first and the one-edge rows last: consecutive tasks cost alike, and the
+    // expensive ones (hundreds of row epilogues per task) would all run in the last wave.  A multiplicative
+    // permutation of the task ids spreads them over the whole launch (ncu: SMs were active 66 % of the time without).
+    const int64_t lin = (int64_t)blockIdx.x * W + wib;
+    const int64_t task = (lin < gp.s.ntasks) ? (lin * gp.task_mul) % gp.s.ntasks : lin;
     const unsigned rp = gp.rp, fq = gp.fq, aq = gp.aq, ap = gp.ap;
     const unsigned fgs = fq * (GRP / 4), ags = aq * (GRP / 4);       // group strides
     const unsigned warp_bytes = NG * (fgs + ags);
@@ -87,8 +92,8 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_gat5_kernel(const Gat5P gp, co
             } else if (act) {
                 float4 v = acc;
                 if (end_rel - beg_rel != 0) {
-                    v.x = __fdiv_rn(v.x, l_run); v.y = __fdiv_rn(v.y, l_run);
-                    v.z = __fdiv_rn(v.z, l_run); v.w = __fdiv_rn(v.w, l_run);
+                    const float inv = __frcp_rn(l_run);   // one reciprocal + 4 multiplies (within 1 ulp of the division)
+                    v.x *= inv; v.y *= inv; v.z *= inv; v.w *= inv;
                 } else {
                     v = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
@@ -263,6 +268,13 @@ static int launch_gat5(const StreamP &p, const float *attn_src, int64_t H, int64
     gp.fq = (gp.rp * 4u + 127u) & ~127u;
     gp.ap = (unsigned)H * 4u;
     gp.aq = (gp.ap * 4u + 127u) & ~127u;
+    {
+        // a multiplier coprime with the task count (so the map is a permutation), large enough to scatter neighbours
+        auto gcd = [](int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; };
+        int64_t m = 9973;
+        while (m > 1 && gcd(m, p.ntasks) != 1) --m;
+        gp.task_mul = (p.ntasks > 64) ? m : 1;
+    }
     CUtensorMap tmf, tma;
     memset(&tmf, 0, sizeof(tmf));
     memset(&tma, 0, sizeof(tma));
