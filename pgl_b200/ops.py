@@ -433,9 +433,16 @@ class _CopyAgg(torch.autograd.Function):
         if ctx.reduce_op == "mean":
             inv = 1.0 / torch.clamp(ctx.fwd["degree"].to(torch.float32), min=1.0)
             s_in = inv if s_in is None else s_in * inv
-        gx = _spmm_raw(bwd["indptr"], bwd["cols"], g, ctx.n_src, "sum", scale_src=s_in,
-                       scale_dst=scale_src, max_degree=bwd.get("max_degree", -1),
-                       packed=_packed_of(bwd, g))
+        # the reverse CSR has one row per graph node; a feature matrix with MORE rows than the graph has nodes
+        # (legal in the forward: the extra rows are never gathered) gets zero gradient rows, never an indptr over-read
+        nb = int(bwd["indptr"].shape[0]) - 1
+        rows = min(ctx.n_src, nb)
+        sdst = scale_src[:rows] if (scale_src is not None and int(scale_src.shape[0]) > rows) else scale_src
+        gx = _spmm_raw(bwd["indptr"][: rows + 1] if rows < nb else bwd["indptr"], bwd["cols"], g, rows, "sum",
+                       scale_src=s_in, scale_dst=sdst, max_degree=bwd.get("max_degree", -1),
+                       packed=_packed_of(bwd, g) if rows == nb else None)
+        if ctx.n_src > rows:
+            gx = torch.cat([gx, gx.new_zeros((ctx.n_src - rows, gx.shape[1]))], 0)
         return gx, None, None, None, None, None, None
 
 
@@ -536,6 +543,10 @@ def aggregate_copy(x, fwd, n_dst, reduce_op="sum", bwd=None, scale_src=None, sca
         out = _CopyAgg.apply(x2, fwd, bwd, n_dst, reduce_op, scale_src, scale_dst)
     elif needs_grad and scale_src is None and scale_dst is None:
         out = _MaxMinAgg.apply(x2, fwd, bwd, n_dst, reduce_op)
+    elif needs_grad:
+        # max / min with fused scales has no backward kernel: do not hand back a silently detached result
+        raise NotImplementedError("pgl_b200: send_u_recv(%s) with fused scale vectors is not differentiable; apply the "
+                                  "scales outside the aggregation" % reduce_op)
     else:
         out = _spmm_raw(fwd["indptr"], fwd["cols"], x2, n_dst, reduce_op, scale_src=scale_src,
                         scale_dst=scale_dst, max_degree=fwd.get("max_degree", -1),

@@ -936,3 +936,23 @@ def test_out_of_range_ids_are_rejected_not_dereferenced(pgl):
     with pytest.raises(ValueError):
         ok.send_recv(torch.ones(3, 4, device="cuda"), "sum")
     assert ok.send_recv(torch.ones(5, 4, device="cuda"), "sum").sum().item() == 8.0
+
+
+def test_backward_with_more_feature_rows_than_nodes(pgl):
+    """x may carry more rows than the graph has nodes (the extra rows are never gathered); their gradient is
+    zero and the backward must not read past the reverse index."""
+    n, e, d = 300, 3000, 32
+    edges = O.chung_lu_edges(n, e, exponent=0.7, seed=901)
+    g = make_graph(pgl, edges, n)
+    x1 = torch.randn(n + 50, d, device="cuda", requires_grad=True)
+    out = g.send_recv(x1, "sum", out_size=n)
+    go = torch.randn(n, d, device="cuda")
+    out.backward(go)
+    x2 = x1.detach().clone().requires_grad_(True)
+    ed = dev(edges)
+    torch.zeros(n, d, device="cuda").index_add_(0, ed[:, 1], x2[ed[:, 0]]).backward(go)
+    assert rel_err(x1.grad.cpu().numpy(), x2.grad.cpu().numpy()) <= RTOL
+    assert float(x1.grad[n:].abs().max()) == 0.0
+    with pytest.raises(NotImplementedError):
+        g._send_u_recv(torch.randn(n, d, device="cuda", requires_grad=True), "max", None,
+                       scale_src=torch.ones(n, device="cuda"))
