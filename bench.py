@@ -495,6 +495,11 @@ def bench_gcn(args, torch, dist, pgl, ops, GF, dev, world, rank):
     n, e, d = args.nodes, args.edges, args.dim
     rr, rc = parse_grid(args, world)
     r, c = rank // rc, rank % rc
+    emu = os.environ.get("PGLB_BENCH_EMULATE", "")   # development aid: "RrxRc:rank" times ONE rank's shard on one GPU
+    if emu and world == 1:
+        gspec, rk = emu.split(":")
+        rr, rc = (int(v) for v in gspec.lower().split("x"))
+        r, c = int(rk) // rc, int(rk) % rc
     assert d % rc == 0 and (d // rc) % 4 == 0, "feature width must split into 16-byte column slices"
     dl = d // rc
     c0 = c * dl

@@ -41,9 +41,7 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_gat5_kernel(const Gat5P gp, co
     __shared__ __align__(8) unsigned long long bars[W * NG];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    // RMAT-like graphs put the hub rows first and the one-edge rows last: consecutive tasks cost alike, and the
-    // expensive ones (hundreds of row epilogues per task) would all run in the last wave.  A multiplicative
-    // permutation of the task ids spreads them over the whole launch (ncu: SMs were active 66 % of the time without).
+    // optional multiplicative permutation of the task ids (task_mul = 1: identity, the default; see launch_gat5)
     const int64_t lin = (int64_t)blockIdx.x * W + wib;
     const int64_t task = (lin < gp.s.ntasks) ? (lin * gp.task_mul) % gp.s.ntasks : lin;
     const unsigned rp = gp.rp, fq = gp.fq, aq = gp.aq, ap = gp.ap;
@@ -268,12 +266,19 @@ static int launch_gat5(const StreamP &p, const float *attn_src, int64_t H, int64
     gp.fq = (gp.rp * 4u + 127u) & ~127u;
     gp.ap = (unsigned)H * 4u;
     gp.aq = (gp.ap * 4u + 127u) & ~127u;
+    // PGLB_GAT_TASK_PERM=1 scatters the task ids with a multiplicative permutation (ncu showed the SMs busy only 66 % of
+    // the launch: RMAT puts the hub rows first and the one-edge rows last).  Measured on cfg3: 2.17 ms without, 2.60 ms
+    // with -- neighbouring tasks share gathered sources in L2 and the permutation throws that away.  Off by default.
     {
-        // a multiplier coprime with the task count (so the map is a permutation), large enough to scatter neighbours
+        static int perm = -1;
+        if (perm < 0) {
+            const char *e = getenv("PGLB_GAT_TASK_PERM");
+            perm = (e && atoi(e) == 1) ? 1 : 0;
+        }
         auto gcd = [](int64_t a, int64_t b) { while (b) { const int64_t t = a % b; a = b; b = t; } return a; };
         int64_t m = 9973;
         while (m > 1 && gcd(m, p.ntasks) != 1) --m;
-        gp.task_mul = (p.ntasks > 64) ? m : 1;
+        gp.task_mul = (perm && p.ntasks > 64) ? m : 1;
     }
     CUtensorMap tmf, tma;
     memset(&tmf, 0, sizeof(tmf));
