@@ -238,6 +238,31 @@ int pglb_gat_fused_csr_f32(const int64_t *indptr, const int64_t *cols, const flo
                            float *out, int64_t ldo, int64_t n_dst, int64_t n_src, int64_t num_edges,
                            int64_t H, int64_t head_dim, void *ws, size_t ws_bytes, void *stream);
 
+/* Training forward of the same layer (GATConv under autograd, pgl/nn/conv.py:333-339; the reference gets the
+ * backward from Paddle autograd over four ops): the same single launch, which also leaves
+ *   lse[d,h] = log sum_j exp(leaky_relu(attn_src[cols[j],h] + attn_dst[d,h]))
+ * for every row with at least one in-edge (other rows of lse are not written).  PGLB_EUNSUPPORTED when the shape is
+ * outside the TMA kernel (H % 4 != 0, slope outside [0, 1], rows not 16-byte aligned): the caller keeps the
+ * op-by-op path, every op of which has a backward. */
+int pglb_gat_fused_train_csr_f32(const int64_t *indptr, const int64_t *cols, const float *f, int64_t ldf,
+                                 const float *attn_src, const float *attn_dst, float negative_slope,
+                                 float *out, int64_t ldo, float *lse, int64_t n_dst, int64_t n_src,
+                                 int64_t num_edges, int64_t H, int64_t head_dim, void *ws, size_t ws_bytes,
+                                 void *stream);
+
+/* Per-edge part of that layer's backward.  rows[j] / cols[j] / eid[j] = destination, source and original edge id
+ * of dst-CSR slot j (EdgeIndex.triples(); eid NULL = identity).  With z = attn_src[src,h] + attn_dst[dst,h]:
+ *   alpha_e[e,h] = exp(leaky_relu(z) - lse[dst,h])                                   (the attention weight, rebuilt)
+ *   dz_e[e,h]    = alpha * (<grad_out[dst,h,:], f[src,h,:]> - <grad_out[dst,h,:], out[dst,h,:]>) * leaky_relu'(z)
+ * both [num_edges, H] in ORIGINAL edge order.  The caller finishes with reverse-CSR aggregations:
+ * grad f = send_ue_recv(grad_out, alpha_e, mul, sum) over the src-keyed CSR, grad attn_src / grad attn_dst = segment
+ * sums of dz_e over the src- / dst-keyed CSR.  head_dim in {4, 8, 16, 32, 64, 128}, H*head_dim <= 128. */
+int pglb_gat_bwd_edge_f32(const int64_t *rows, const int64_t *cols, const int64_t *eid, const float *f,
+                          int64_t ldf, const float *grad_out, int64_t ldg, const float *out, int64_t ldo,
+                          const float *attn_src, const float *attn_dst, const float *lse,
+                          float negative_slope, int64_t num_edges, int64_t H, int64_t head_dim,
+                          float *alpha_e, float *dz_e, void *stream);
+
 /* out[M, N] = act(x[M, K] @ w[K, N] + bias[N]) -- the dense transform of the conv layers
  * (pgl/nn/conv.py:238-251 GCNConv: `self.linear(...)`, `+ self.bias`, activation; the same Linear in
  * GATConv :321 / GraphSageConv :107-108) on the tensor cores with 3xTF32 error compensation (fp32-level

@@ -4,6 +4,8 @@
 //   * send_ue_recv(mul) wrt the edge operand = per-head dot of x[src] and grad[dst]  (sddmm_dot)
 //   * edge_softmax backward                 = alpha * (g - sum_row(alpha * g))
 //   * max / min copy aggregation backward   = grad routed to the entries that equal the output
+//   * fused GAT aggregation backward        = one edge kernel (attention weights rebuilt from the saved row
+//     log-sum-exp, SDDMM dot, softmax / LeakyReLU backward) + the existing reverse-CSR aggregations
 #include "common.cuh"
 
 namespace pglb {
@@ -95,6 +97,94 @@ __global__ void __launch_bounds__(256) maxmin_bwd_kernel(const int64_t *__restri
     }
 }
 
+
+// Backward of the single-pass GAT aggregation (pglb_gat_fused_train_csr_f32), the per-edge part.  With
+//   z = as[src,h] + ad[dst,h],  lz = leaky_relu(z),  alpha = exp(lz - lse[dst,h]),  out[dst,h,:] = sum alpha f[src,h,:]
+// and G = d loss / d out:
+//   d alpha = <G[dst,h,:], f[src,h,:]>,   d lz = alpha (d alpha - <G[dst,h,:], out[dst,h,:]>),   d z = d lz * leaky'(z).
+// One launch rebuilds alpha and produces dz for every edge, both written in ORIGINAL edge order, which is what the
+// reverse-CSR aggregations that finish the job read (grad f = sum over out-edges alpha G[dst]; grad as / grad ad =
+// segment sums of dz over the src- / dst-CSR, exactly send_uv(add)'s backward).  Neither logits nor alpha were kept by
+// the forward.  Walks the dst-CSR slots (rows[] = destination of every slot, so G / out / ad / lse are re-read only when
+// the row changes); a warp owns 32 consecutive slots, the D/4 active lanes hold one float4 of the row each, LPH = Dh/4
+// lanes form a head; four gathered feature rows are in flight per lane before the first dot product.
+template <int LPH>
+__global__ void __launch_bounds__(256) gat_bwd_edge_kernel(
+    const int64_t *__restrict__ rows, const int64_t *__restrict__ cols, const int64_t *__restrict__ eid,
+    const float *__restrict__ f, int64_t ldf, const float *__restrict__ g, int64_t ldg,
+    const float *__restrict__ out, int64_t ldo, const float *__restrict__ a_s, const float *__restrict__ a_d,
+    const float *__restrict__ lse, float slope, int64_t E, int H, int D, float *__restrict__ alpha_e,
+    float *__restrict__ dz_e) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool act = lane * 4 < D;
+    const int head = act ? lane / LPH : 0;
+    const bool lead = act && (lane % LPH) == 0;
+    auto head_sum = [&](float v) {
+#pragma unroll
+        for (int o = LPH / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    };
+    auto dot4 = [](const float4 &a, const float4 &b) {
+        return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
+    };
+    for (int64_t base = warp * 32; base < E; base += nwarps * 32) {
+        const int64_t j = base + lane;
+        const bool in = j < E;
+        const long long r_l = in ? ld_stream(rows + j) : 0;
+        const long long c_l = in ? ld_stream(cols + j) : 0;
+        const long long i_l = in ? (eid ? ld_stream(eid + j) : j) : 0;
+        const int cnt = (E - base) < 32 ? (int)(E - base) : 32;
+        long long cur = -1;
+        float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float ad = 0.f, ls = 0.f, delta = 0.f;
+        for (int k0 = 0; k0 < cnt; k0 += 4) {
+            float4 fv[4];
+            float as[4];
+            long long rr[4], ii[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = (k0 + u) & 31;
+                const long long cc = __shfl_sync(0xffffffffu, c_l, k);
+                rr[u] = __shfl_sync(0xffffffffu, r_l, k);
+                ii[u] = __shfl_sync(0xffffffffu, i_l, k);
+                fv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                as[u] = 0.f;
+                if (k0 + u < cnt && act) {
+                    fv[u] = __ldg(reinterpret_cast<const float4 *>(f + cc * ldf + lane * 4));
+                    as[u] = __ldg(a_s + cc * H + head);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (k0 + u >= cnt) break;
+                if (rr[u] != cur) {  // warp-uniform
+                    cur = rr[u];
+                    float d = 0.f;
+                    if (act) {
+                        g4 = __ldg(reinterpret_cast<const float4 *>(g + cur * ldg + lane * 4));
+                        const float4 o4 = __ldg(reinterpret_cast<const float4 *>(out + cur * ldo + lane * 4));
+                        ad = __ldg(a_d + cur * H + head);
+                        ls = __ldg(lse + cur * H + head);
+                        d = dot4(g4, o4);
+                    }
+                    delta = head_sum(d);
+                }
+                const float da = head_sum(dot4(fv[u], g4));
+                const float z = as[u] + ad;
+                const bool pos = z >= 0.0f;
+                const float alpha = expf((pos ? z : z * slope) - ls);
+                const float dl = alpha * (da - delta);
+                if (lead) {
+                    alpha_e[ii[u] * H + head] = alpha;
+                    dz_e[ii[u] * H + head] = pos ? dl : dl * slope;
+                }
+            }
+        }
+    }
+}
+
 static inline int grid_of(int64_t total, int cap_mult) {
     int64_t b = (total + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * cap_mult;
@@ -144,6 +234,42 @@ extern "C" int pglb_edge_softmax_bwd_csr_f32(const int64_t *indptr, const int64_
     edge_softmax_bwd_kernel<<<grid, 256, 0, stream>>>(indptr, eid, alpha, grad, grad_logits, n_rows,
                                                       (int)H, hp);
     PGLB_LAUNCH_CHECK("edge_softmax_bwd_kernel");
+    return PGLB_OK;
+}
+
+extern "C" int pglb_gat_bwd_edge_f32(const int64_t *rows, const int64_t *cols, const int64_t *eid, const float *f,
+                                     int64_t ldf, const float *grad_out, int64_t ldg, const float *out, int64_t ldo,
+                                     const float *attn_src, const float *attn_dst, const float *lse,
+                                     float negative_slope, int64_t num_edges, int64_t H, int64_t head_dim,
+                                     float *alpha_e, float *dz_e, void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    PGLB_CHECK_ARG(num_edges >= 0 && H > 0 && head_dim > 0, PGLB_EINVAL, "pglb_gat_bwd_edge_f32: bad size");
+    const int64_t D = H * head_dim;
+    const int64_t lph = head_dim / 4;
+    PGLB_CHECK_ARG(D <= 128 && head_dim % 4 == 0 && (lph & (lph - 1)) == 0, PGLB_EUNSUPPORTED,
+                   "pglb_gat_bwd_edge_f32: needs H*head_dim <= 128 and head_dim in {4, 8, 16, 32, 64, 128}");
+    if (num_edges == 0) return PGLB_OK;
+    PGLB_CHECK_ARG(rows && cols && f && grad_out && out && attn_src && attn_dst && lse && alpha_e && dz_e, PGLB_EINVAL,
+                   "pglb_gat_bwd_edge_f32: NULL pointer");
+    auto a16 = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    PGLB_CHECK_ARG(ldf >= D && ldg >= D && ldo >= D && ldf % 4 == 0 && ldg % 4 == 0 && ldo % 4 == 0 && a16(f) &&
+                       a16(grad_out) && a16(out),
+                   PGLB_ESHAPE, "pglb_gat_bwd_edge_f32: rows must be 16-byte aligned");
+    const int grid = grid_of(num_edges * 1, 64);  // a warp per 32 slots, grid-stride
+#define PGLB_GBE(L)                                                                                                   \
+    gat_bwd_edge_kernel<L><<<grid, 256, 0, stream>>>(rows, cols, eid, f, ldf, grad_out, ldg, out, ldo, attn_src,      \
+                                                    attn_dst, lse, negative_slope, num_edges, (int)H, (int)D,        \
+                                                    alpha_e, dz_e)
+    switch ((int)lph) {
+        case 1: PGLB_GBE(1); break;
+        case 2: PGLB_GBE(2); break;
+        case 4: PGLB_GBE(4); break;
+        case 8: PGLB_GBE(8); break;
+        case 16: PGLB_GBE(16); break;
+        default: PGLB_GBE(32); break;
+    }
+#undef PGLB_GBE
+    PGLB_LAUNCH_CHECK("gat_bwd_edge_kernel");
     return PGLB_OK;
 }
 

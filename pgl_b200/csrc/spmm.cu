@@ -423,7 +423,7 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
 
 int gat_fused_run(const int64_t *indptr, const int64_t *cols, const float *f, int64_t ldf, float *out,
                   int64_t ldo, int64_t n_dst, int64_t n_src, int64_t E, int64_t D, int64_t H,
-                  const float *attn_src, const float *attn_dst, float slope, void *ws, size_t ws_bytes,
+                  const float *attn_src, const float *attn_dst, float slope, float *lse, void *ws, size_t ws_bytes,
                   cudaStream_t stream);
 
 bool stream_narrow_enabled();  // PGLB_NARROW=1: experimental narrow-row streaming kernel (spmm_stream.cu)
@@ -611,29 +611,48 @@ extern "C" int pglb_spmm_csr_f32(const int64_t *indptr, const int64_t *cols, con
     return PGLB_OK;
 }
 
+static int gat_fused_entry(const char *name, const int64_t *indptr, const int64_t *cols, const float *f, int64_t ldf,
+                           const float *attn_src, const float *attn_dst, float negative_slope, float *out, int64_t ldo,
+                           float *lse, int64_t n_dst, int64_t n_src, int64_t num_edges, int64_t H, int64_t head_dim,
+                           void *ws, size_t ws_bytes, void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    PGLB_CHECK_ARG(n_dst >= 0 && n_src >= 0 && num_edges >= 0 && H > 0 && head_dim > 0, PGLB_EINVAL, "%s: bad size", name);
+    const int64_t D = H * head_dim;
+    PGLB_CHECK_ARG(D <= 128 && head_dim % 4 == 0 && num_edges < 0x7fffffffLL && n_src < 0xffffffffLL,
+                   PGLB_EUNSUPPORTED, "%s: needs H*head_dim <= 128 and head_dim %% 4 == 0", name);
+    if (n_dst == 0) return PGLB_OK;
+    PGLB_CHECK_ARG(indptr && out, PGLB_EINVAL, "%s: NULL pointer", name);
+    PGLB_CHECK_ARG(ldf >= D && ldo >= D && ldf % 4 == 0 && ldo % 4 == 0 && aligned16(f) && aligned16(out),
+                   PGLB_ESHAPE, "%s: rows must be 16-byte aligned", name);
+    if (num_edges == 0) {
+        PGLB_CUDA(cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * D, n_dst, stream));
+        return PGLB_OK;
+    }
+    PGLB_CHECK_ARG(cols && f && attn_src && attn_dst, PGLB_EINVAL, "%s: NULL pointer", name);
+    PGLB_CHECK_ARG(ws && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, PGLB_EWORKSPACE,
+                   "%s: workspace NULL or not 256-byte aligned", name);
+    return gat_fused_run(indptr, cols, f, ldf, out, ldo, n_dst, n_src, num_edges, D, H, attn_src,
+                         attn_dst, negative_slope, lse, ws, ws_bytes, stream);
+}
+
 extern "C" int pglb_gat_fused_csr_f32(const int64_t *indptr, const int64_t *cols, const float *f,
                                       int64_t ldf, const float *attn_src, const float *attn_dst,
                                       float negative_slope, float *out, int64_t ldo, int64_t n_dst,
                                       int64_t n_src, int64_t num_edges, int64_t H, int64_t head_dim,
                                       void *ws, size_t ws_bytes, void *stream_) {
-    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    PGLB_CHECK_ARG(n_dst >= 0 && n_src >= 0 && num_edges >= 0 && H > 0 && head_dim > 0, PGLB_EINVAL,
-                   "pglb_gat_fused_csr_f32: bad size");
-    const int64_t D = H * head_dim;
-    PGLB_CHECK_ARG(D <= 128 && head_dim % 4 == 0 && num_edges < 0x7fffffffLL && n_src < 0xffffffffLL,
-                   PGLB_EUNSUPPORTED,
-                   "pglb_gat_fused_csr_f32: needs H*head_dim <= 128 and head_dim %% 4 == 0");
-    if (n_dst == 0) return PGLB_OK;
-    PGLB_CHECK_ARG(indptr && out, PGLB_EINVAL, "pglb_gat_fused_csr_f32: NULL pointer");
-    PGLB_CHECK_ARG(ldf >= D && ldo >= D && ldf % 4 == 0 && ldo % 4 == 0 && aligned16(f) && aligned16(out),
-                   PGLB_ESHAPE, "pglb_gat_fused_csr_f32: rows must be 16-byte aligned");
-    if (num_edges == 0) {
-        PGLB_CUDA(cudaMemset2DAsync(out, sizeof(float) * ldo, 0, sizeof(float) * D, n_dst, stream));
-        return PGLB_OK;
-    }
-    PGLB_CHECK_ARG(cols && f && attn_src && attn_dst, PGLB_EINVAL, "pglb_gat_fused_csr_f32: NULL pointer");
-    PGLB_CHECK_ARG(ws && (reinterpret_cast<uintptr_t>(ws) & 255u) == 0, PGLB_EWORKSPACE,
-                   "pglb_gat_fused_csr_f32: workspace NULL or not 256-byte aligned");
-    return gat_fused_run(indptr, cols, f, ldf, out, ldo, n_dst, n_src, num_edges, D, H, attn_src,
-                         attn_dst, negative_slope, ws, ws_bytes, stream);
+    return gat_fused_entry("pglb_gat_fused_csr_f32", indptr, cols, f, ldf, attn_src, attn_dst, negative_slope, out, ldo,
+                           nullptr, n_dst, n_src, num_edges, H, head_dim, ws, ws_bytes, stream_);
+}
+
+// Training forward: the same launch, which additionally leaves lse[d, h] = log sum_j exp(leaky(as[src_j,h] + ad[d,h]))
+// for every row with at least one in-edge (rows without are not written) -- all pglb_gat_bwd_edge_f32 needs to rebuild
+// the attention weights.  PGLB_EUNSUPPORTED when the shape is outside the TMA kernel (the caller keeps the op-by-op path).
+extern "C" int pglb_gat_fused_train_csr_f32(const int64_t *indptr, const int64_t *cols, const float *f,
+                                            int64_t ldf, const float *attn_src, const float *attn_dst,
+                                            float negative_slope, float *out, int64_t ldo, float *lse,
+                                            int64_t n_dst, int64_t n_src, int64_t num_edges, int64_t H,
+                                            int64_t head_dim, void *ws, size_t ws_bytes, void *stream_) {
+    PGLB_CHECK_ARG(lse != nullptr || n_dst == 0, PGLB_EINVAL, "pglb_gat_fused_train_csr_f32: NULL lse");
+    return gat_fused_entry("pglb_gat_fused_train_csr_f32", indptr, cols, f, ldf, attn_src, attn_dst, negative_slope, out,
+                           ldo, lse, n_dst, n_src, num_edges, H, head_dim, ws, ws_bytes, stream_);
 }

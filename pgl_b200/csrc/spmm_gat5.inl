@@ -31,7 +31,7 @@ struct Gat5P {
     int64_t task_mul; // task id = (linear warp id * task_mul) % ntasks, gcd(task_mul, ntasks) == 1
 };
 
-template <int GRP, int NG, int W>
+template <int GRP, int NG, int W, bool DYN>
 __global__ void __launch_bounds__(W * 32, 2) spmm_gat5_kernel(const Gat5P gp, const __grid_constant__ CUtensorMap tmf,
                                                               const __grid_constant__ CUtensorMap tma) {
     typedef GeoG5<GRP, NG, W> G_;
@@ -43,7 +43,6 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_gat5_kernel(const Gat5P gp, co
     const int wib = threadIdx.x >> 5;
     // optional multiplicative permutation of the task ids (task_mul = 1: identity, the default; see launch_gat5)
     const int64_t lin = (int64_t)blockIdx.x * W + wib;
-    const int64_t task = (lin < gp.s.ntasks) ? (lin * gp.task_mul) % gp.s.ntasks : lin;
     const unsigned rp = gp.rp, fq = gp.fq, aq = gp.aq, ap = gp.ap;
     const unsigned fgs = fq * (GRP / 4), ags = aq * (GRP / 4);       // group strides
     const unsigned warp_bytes = NG * (fgs + ags);
@@ -57,12 +56,27 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_gat5_kernel(const Gat5P gp, co
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    if (task >= p.ntasks) return;
+    if (!DYN && lin >= p.ntasks) return;
     const bool act = lane * 4 < p.D;
     const unsigned lane_off = act ? lane * 16 : 0;
     const int yhead = act ? (lane * 4) / p.head_dim : 0;
+    const bool hlead = act && p.lse != nullptr && (lane * 4) % p.head_dim == 0;  // first lane of a head: writes lse
     const float slope = p.slope;
 
+    // DYN: persistent warps draw task ids from the device counter task_plan_kernel zeroed (see spmm_v5_kernel)
+    unsigned gtot = 0;  // groups pushed through this warp's mbarrier ring by earlier tasks
+#pragma unroll 1
+    for (;;) {
+    int64_t task;
+    if (DYN) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(p.counter, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if ((int64_t)t >= p.ntasks) break;
+        task = p.dyn == 2 ? p.ntasks - 1 - (int64_t)t : (int64_t)t;
+    } else {
+        task = (lin * gp.task_mul) % p.ntasks;
+    }
     const int64_t a = ld_ro(p.start + task);
     const int64_t b = ld_ro(p.start + task + 1);
     const int cnt = (int)(b - a);
@@ -96,6 +110,7 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_gat5_kernel(const Gat5P gp, co
                     v = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 __stcs(reinterpret_cast<float4 *>(p.out + row * p.ldo + lane * 4), v);
+                if (hlead) p.lse[row * p.ldy + yhead] = m_run + logf(l_run);
             }
             ++row;
             beg_rel = end_rel;
@@ -155,7 +170,7 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_gat5_kernel(const Gat5P gp, co
                     col_cur = col_nxt;
                     col_nxt = load_col(g / GPB + 1);
                 }
-                const int s = g % NG;
+                const int s = (int)((gtot + (unsigned)g) % NG);
                 __syncwarp();  // every lane has finished reading slot s (consumed NG groups ago)
                 if (lane == 0) mbar_expect_tx(bar0 + s * 8, GRP * (rp + ap));
 #pragma unroll
@@ -172,9 +187,9 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_gat5_kernel(const Gat5P gp, co
             }
             if (g >= LAG) {
                 const int gc = g - LAG;
-                const int s = gc % NG;
+                const int s = (int)((gtot + (unsigned)gc) % NG);
                 const int base = gc * GRP;
-                mbar_wait(bar0 + s * 8, (unsigned)((gc / NG) & 1));
+                mbar_wait(bar0 + s * 8, ((gtot + (unsigned)gc) / NG) & 1u);
                 int valid = cnt - base;
                 valid = valid > GRP ? GRP : valid;
                 const unsigned fg = fring + s * fgs + lane_off;
@@ -219,8 +234,11 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_gat5_kernel(const Gat5P gp, co
             p.partial_ml[sl * 64 + lane * 2 + 1] = l_run;
             if (!head) tail = row;
         }
+        if (DYN) gtot += (unsigned)ngroups;
     }
     if (lane == 0) p.tail_row[task] = tail;
+    if (!DYN) break;
+    }
 }
 
 // PGLB_GAT_V5 = 0 keeps round 1's fused kernel
@@ -245,13 +263,21 @@ static bool gat5_eligible(const StreamP &p, const float *f, int64_t ldf, const f
 template <int GRP, int NG, int W>
 static int launch_gat5_geo(const Gat5P &gp, const CUtensorMap &tmf, const CUtensorMap &tma, cudaStream_t stream) {
     const int smem = W * NG * (int)((gp.fq + gp.aq) * (GRP / 4)) + 128;
-    static std::atomic<unsigned long long> attr_done{0};
-    PGLB_CUDA(ensure_dyn_smem(spmm_gat5_kernel<GRP, NG, W>, 112 * 1024, attr_done));
     PGLB_CHECK_ARG(smem <= 112 * 1024, PGLB_ESHAPE, "spmm_gat5: shared memory budget exceeded");
     const StreamP &p = gp.s;
-    const int64_t blocks = (p.ntasks + W - 1) / W;
+    int64_t blocks = (p.ntasks + W - 1) / W;
     PGLB_CHECK_ARG(blocks <= 0x7fffffffLL, PGLB_ESHAPE, "spmm_gat5: grid too large");
-    spmm_gat5_kernel<GRP, NG, W><<<(unsigned)blocks, W * 32, smem, stream>>>(gp, tmf, tma);
+    if (p.dyn) {
+        static std::atomic<unsigned long long> attr_done_dyn{0};
+        PGLB_CUDA(ensure_dyn_smem(spmm_gat5_kernel<GRP, NG, W, true>, 112 * 1024, attr_done_dyn));
+        const int64_t resident = (int64_t)sm_count() * 2;  // __launch_bounds__(W * 32, 2), <= 112 KB of rings per CTA
+        if (blocks > resident) blocks = resident;
+        spmm_gat5_kernel<GRP, NG, W, true><<<(unsigned)blocks, W * 32, smem, stream>>>(gp, tmf, tma);
+    } else {
+        static std::atomic<unsigned long long> attr_done{0};
+        PGLB_CUDA(ensure_dyn_smem(spmm_gat5_kernel<GRP, NG, W, false>, 112 * 1024, attr_done));
+        spmm_gat5_kernel<GRP, NG, W, false><<<(unsigned)blocks, W * 32, smem, stream>>>(gp, tmf, tma);
+    }
     PGLB_LAUNCH_CHECK("spmm_gat5_kernel");
     const int64_t fblocks = (p.ntasks * 32 + 255) / 256;
     spmm_stream_fixup_gat_kernel<<<(unsigned)fblocks, 256, 0, stream>>>(p);

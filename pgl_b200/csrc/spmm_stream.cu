@@ -66,6 +66,9 @@ struct StreamP {
     float *partial_ml;       // YM 2: [2*ntasks, 64] running (max, sum) of cut rows, per lane
     int accumulate;          // SUM only: out = (out_prev + sum) * scale_dst
     int hot_mode;            // 1: hot=evict_last cold=evict_first, 2: hot=last cold=normal, 3: hot=normal cold=first
+    unsigned *counter;       // task queue head of the persistent (DYN) kernels, zeroed by task_plan_kernel
+    float *lse;              // YM 2, nullable: [n_rows, H] log-sum-exp of every non-empty row's logits (saved for backward)
+    int dyn;                 // 0: static block -> task map, 1: dynamic ascending, 2: dynamic descending
 };
 
 __device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc) {
@@ -134,11 +137,13 @@ __global__ void __launch_bounds__(256) task_plan_kernel(const int64_t *__restric
                                                         int64_t n_rows, int64_t E, int64_t T,
                                                         int64_t snap, int64_t ntasks,
                                                         int64_t *__restrict__ first_row,
-                                                        int64_t *__restrict__ start) {
+                                                        int64_t *__restrict__ start,
+                                                        unsigned *__restrict__ counter) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t > ntasks) return;
     if (t == ntasks) {
         start[t] = E;
+        if (counter) *counter = 0u;
         return;
     }
     if (t == 0) {
@@ -711,6 +716,7 @@ __global__ void __launch_bounds__(256) spmm_stream_fixup_gat_kernel(const Stream
     acc.x = __fdiv_rn(acc.x, L); acc.y = __fdiv_rn(acc.y, L);
     acc.z = __fdiv_rn(acc.z, L); acc.w = __fdiv_rn(acc.w, L);
     *reinterpret_cast<float4 *>(p.out + r * p.ldo + c) = acc;
+    if (p.lse && c % p.head_dim == 0) p.lse[r * p.ldy + c / p.head_dim] = M + logf(L);
 }
 
 // Rows without a slot: zero (or, when accumulating, out_prev * scale_dst).  One warp looks at 32
@@ -1013,6 +1019,7 @@ struct StreamWs {
     int64_t *tail_row;
     float *partial;
     float *partial_ml;
+    unsigned *counter;
     int64_t ntasks, dpad;
     size_t bytes;
 };
@@ -1033,6 +1040,7 @@ static StreamWs stream_layout(void *ws, int64_t E, int64_t D, int64_t T) {
     w.tail_row = reinterpret_cast<int64_t *>(take(sizeof(int64_t) * w.ntasks));
     w.partial = reinterpret_cast<float *>(take(sizeof(float) * 2 * w.ntasks * w.dpad));
     w.partial_ml = reinterpret_cast<float *>(take(sizeof(float) * 2 * w.ntasks * 64));
+    w.counter = reinterpret_cast<unsigned *>(take(sizeof(unsigned)));
     w.bytes = off;
     return w;
 }
@@ -1068,6 +1076,16 @@ int64_t stream_task_size(int64_t E) {
 static int64_t stream_snap(int64_t T) { return env_task_size() ? T : (T > 1024 ? T : 1024); }
 
 size_t stream_ws_bytes(int64_t E, int64_t D) { return stream_layout(nullptr, E, D, stream_task_size(E)).bytes; }
+
+// Task hand-out of the persistent kernels (spmm_v5 / spmm_gat5): 0 = static block -> task map, 1 = device-side queue
+// in ascending task order, 2 = queue in descending order.  slot 0: PGLB_V5_DYN, slot 1: PGLB_GAT_DYN.
+// Read per call (a getenv, no cache) so one process can compare the modes.
+static int dyn_mode(const char *name, int slot) {
+    static const int defaults[2] = {0, 0};
+    const char *e = getenv(name);
+    const int v = e ? atoi(e) : defaults[slot];
+    return (v < 0 || v > 2) ? defaults[slot] : v;
+}
 
 static int stream_cfg() {
     static int c = -1;
@@ -1171,10 +1189,12 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
         }
         p.hot_mode = mode;
     }
+    p.counter = w.counter;
+    p.dyn = dyn_mode("PGLB_V5_DYN", 0);
     {
         const int64_t blocks = (w.ntasks + 1 + 255) / 256;
         task_plan_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indptr, n_dst, E, T, stream_snap(T),
-                                                               w.ntasks, w.first_row, w.start);
+                                                               w.ntasks, w.first_row, w.start, w.counter);
         PGLB_LAUNCH_CHECK("task_plan_kernel");
     }
     {
@@ -1330,7 +1350,7 @@ int narrow2_run(const uint32_t *plan, const int32_t *nz_row, const int32_t *blk_
 // Single-pass GAT aggregation (inference): out[d,h,:] = sum_j softmax_j(leaky(as[src_j,h] + ad[d,h])) f[src_j,h,:]
 int gat_fused_run(const int64_t *indptr, const int64_t *cols, const float *f, int64_t ldf, float *out,
                   int64_t ldo, int64_t n_dst, int64_t n_src, int64_t E, int64_t D, int64_t H,
-                  const float *attn_src, const float *attn_dst, float slope, void *ws, size_t ws_bytes,
+                  const float *attn_src, const float *attn_dst, float slope, float *lse, void *ws, size_t ws_bytes,
                   cudaStream_t stream) {
     const int64_t T = stream_task_size(E);
     PGLB_CHECK_ARG(E > 0, PGLB_EINVAL, "gat_fused_run: needs at least one slot");
@@ -1363,10 +1383,16 @@ int gat_fused_run(const int64_t *indptr, const int64_t *cols, const float *f, in
     p.attn_dst = attn_dst;
     p.slope = slope;
     p.hot_mode = 1;
+    p.counter = w.counter;
+    p.dyn = dyn_mode("PGLB_GAT_DYN", 1);
+    p.lse = lse;
+    // the row statistics are written by spmm_gat5_kernel and the merge kernel only
+    PGLB_CHECK_ARG(!lse || gat5_eligible(p, f, ldf, attn_src, H, n_src), PGLB_EUNSUPPORTED,
+                   "pglb_gat_fused_train_csr_f32: shape outside the TMA kernel (H %% 4, 16-byte rows, 0 <= slope <= 1)");
     {
         const int64_t blocks = (w.ntasks + 1 + 255) / 256;
         task_plan_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indptr, n_dst, E, T, stream_snap(T),
-                                                               w.ntasks, w.first_row, w.start);
+                                                               w.ntasks, w.first_row, w.start, w.counter);
         PGLB_LAUNCH_CHECK("task_plan_kernel");
     }
     {

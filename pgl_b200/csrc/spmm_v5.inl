@@ -76,7 +76,10 @@ struct GeoV5 {
     static constexpr int kSmem = W_ * kWarpBytes + 128;  // +128: manual alignment of the dynamic base
 };
 
-template <int ISSUE, bool SCALED, bool D128, bool HOT, int GRP, int NG, int W>
+// DYN: persistent warps draw task ids from a device counter (zeroed by task_plan_kernel) instead of the static
+// block -> task map: a warp that finishes early takes the next task, so no SM idles while a neighbour's slowest warp
+// finishes (p.dyn == 2 hands the ids out from the last task down).  Results do not depend on which warp ran a task.
+template <int ISSUE, bool SCALED, bool D128, bool HOT, int GRP, int NG, int W, bool DYN>
 __global__ void __launch_bounds__(W * 32, 2) spmm_v5_kernel(const StreamP p, const __grid_constant__ CUtensorMap tm) {
     typedef GeoV5<GRP, NG, W> G_;
     constexpr int LAG = G_::kLag, GPB = G_::kGpb;
@@ -85,7 +88,6 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_v5_kernel(const StreamP p, con
     __shared__ __align__(8) unsigned long long bars[W * NG];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const int64_t task = (int64_t)blockIdx.x * W + wib;
     const unsigned smem0 = ((unsigned)__cvta_generic_to_shared(smem_dyn) + 127u) & ~127u;
     const unsigned ring0 = smem0 + wib * G_::kWarpBytes;       // NG*GRP rows
     const unsigned sring = ring0 + NG * GRP * 512;              // 128 floats: norms of 4 column batches
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_v5_kernel(const StreamP p, con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncwarp();
     }
-    if (task >= p.ntasks) return;
+    if (!DYN && (int64_t)blockIdx.x * W + wib >= p.ntasks) return;
     // HOT: bit 31 of the packed ids marks the most frequently gathered sources (pglb_pack_cols); a quad that holds
     // one is fetched with the "keep" policy, a quad of cold rows with evict_first so the long tail cannot flush them
     const uint64_t pol_keep = !HOT ? 0 : (p.hot_mode == 3 ? policy_evict_normal() : policy_evict_last());
@@ -113,6 +115,19 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_v5_kernel(const StreamP p, con
     const char *xlane = reinterpret_cast<const char *>(p.x) + lane_off;
     const unsigned row_bytes = (unsigned)(p.ldx * 4);
 
+    unsigned gtot = 0;  // groups this warp has pushed through its mbarrier ring in earlier tasks (DYN, ISSUE 1)
+#pragma unroll 1
+    for (;;) {
+    int64_t task;
+    if (DYN) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(p.counter, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);  // also: every lane has left the previous task's rings
+        if ((int64_t)t >= p.ntasks) break;
+        task = p.dyn == 2 ? p.ntasks - 1 - (int64_t)t : (int64_t)t;
+    } else {
+        task = (int64_t)blockIdx.x * W + wib;
+    }
     const int64_t a = ld_ro(p.start + task);
     const int64_t b = ld_ro(p.start + task + 1);
     const int cnt = (int)(b - a);
@@ -201,7 +216,7 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_v5_kernel(const StreamP p, con
                         if (ISSUE == 1) cp_async_commit();
                     }
                 }
-                const int s = g % NG;
+                const int s = (int)((gtot + (unsigned)g) % NG);
                 if (ISSUE == 1) {
                     __syncwarp();  // every lane has finished reading slot s (consumed NG groups ago)
                     if (lane == 0) mbar_expect_tx(bar0 + s * 8, GRP * rp);
@@ -237,14 +252,14 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_v5_kernel(const StreamP p, con
             if (ISSUE == 0) cp_async_commit();
             if (g >= LAG) {
                 const int gc = g - LAG;
-                const int s = gc % NG;
+                const int s = (int)((gtot + (unsigned)gc) % NG);
                 const int base = gc * GRP;
                 if (ISSUE == 1) {
                     if (SCALED && (gc % GPB) == 0) {
                         cp_async_wait<0>();  // this batch's norms (the only cp.async traffic of this variant)
                         __syncwarp();
                     }
-                    mbar_wait(bar0 + s * 8, (unsigned)((gc / NG) & 1));
+                    mbar_wait(bar0 + s * 8, ((gtot + (unsigned)gc) / NG) & 1u);
                 } else {
                     cp_async_wait<LAG>();
                     if (SCALED && (gc % GPB) == 0) __syncwarp();  // norms were written by other lanes
@@ -318,8 +333,11 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_v5_kernel(const StreamP p, con
                 *reinterpret_cast<float4 *>(p.partial + (head ? (2 * task) : (2 * task + 1)) * p.dpad + lane * 4) = acc;
             if (!head) tail = row;
         }
+        if (DYN && ISSUE == 1) gtot += (unsigned)ngroups;
     }
     if (lane == 0) p.tail_row[task] = tail;
+    if (!DYN) break;
+    }
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
@@ -380,11 +398,24 @@ static int v5_geo() {
 template <int ISSUE, bool SCALED, bool D128, bool HOT, int GRP, int NG, int W>
 static int launch_v5_geo(const StreamP &p, const CUtensorMap &tm, cudaStream_t stream) {
     typedef GeoV5<GRP, NG, W> G_;
-    static std::atomic<unsigned long long> attr_done{0};
-    PGLB_CUDA(ensure_dyn_smem(spmm_v5_kernel<ISSUE, SCALED, D128, HOT, GRP, NG, W>, G_::kSmem, attr_done));
-    const int64_t blocks = (p.ntasks + W - 1) / W;
+    int64_t blocks = (p.ntasks + W - 1) / W;
     PGLB_CHECK_ARG(blocks <= 0x7fffffffLL, PGLB_ESHAPE, "spmm_v5: grid too large");
-    spmm_v5_kernel<ISSUE, SCALED, D128, HOT, GRP, NG, W><<<(unsigned)blocks, W * 32, G_::kSmem, stream>>>(p, tm);
+    bool launched = false;
+    if constexpr (ISSUE == 1) {
+      if (p.dyn) {
+        static std::atomic<unsigned long long> attr_done_dyn{0};
+        PGLB_CUDA(ensure_dyn_smem(spmm_v5_kernel<ISSUE, SCALED, D128, HOT, GRP, NG, W, true>, G_::kSmem, attr_done_dyn));
+        const int64_t resident = (int64_t)sm_count() * 2;  // __launch_bounds__(W * 32, 2)
+        if (blocks > resident) blocks = resident;
+        spmm_v5_kernel<ISSUE, SCALED, D128, HOT, GRP, NG, W, true><<<(unsigned)blocks, W * 32, G_::kSmem, stream>>>(p, tm);
+        launched = true;
+      }
+    }
+    if (!launched) {
+        static std::atomic<unsigned long long> attr_done{0};
+        PGLB_CUDA(ensure_dyn_smem(spmm_v5_kernel<ISSUE, SCALED, D128, HOT, GRP, NG, W, false>, G_::kSmem, attr_done));
+        spmm_v5_kernel<ISSUE, SCALED, D128, HOT, GRP, NG, W, false><<<(unsigned)blocks, W * 32, G_::kSmem, stream>>>(p, tm);
+    }
     PGLB_LAUNCH_CHECK("spmm_v5_kernel");
     const int64_t fblocks = (p.ntasks * 32 + 255) / 256;
     spmm_stream_fixup_kernel<1, 0><<<(unsigned)fblocks, 256, 0, stream>>>(p);

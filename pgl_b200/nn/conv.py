@@ -204,13 +204,21 @@ class GATConv(nn.Module):
             if self.activation is not None:
                 output = self.activation(output)
             return output
-        alpha = graph.send_uv(attn_src, attn_dst, "add")
-        alpha = self.leaky_relu(alpha)
-        alpha = GF.edge_softmax(graph, alpha)
-        alpha = alpha.reshape(-1, self.num_heads, 1)
-        if self.attn_drop > 1e-15:
-            alpha = self.attn_dropout(alpha)
-        output = graph.send_ue_recv(feature, alpha, "mul", "sum")
+        output = None
+        if no_attn_drop and type(graph).__name__ == "Graph" and feature.dtype == torch.float32:
+            # training without attention dropout: the same single-pass kernel, which keeps the rows' log-sum-exp, and
+            # a fused backward (ops._GatFused); None when the shape is outside it
+            from .. import ops
+            output = ops.gat_fused_train(graph._fwd_csr(), graph._bwd_csr, feature, attn_src, attn_dst,
+                                         self.leaky_relu.negative_slope)
+        if output is None:
+            alpha = graph.send_uv(attn_src, attn_dst, "add")
+            alpha = self.leaky_relu(alpha)
+            alpha = GF.edge_softmax(graph, alpha)
+            alpha = alpha.reshape(-1, self.num_heads, 1)
+            if self.attn_drop > 1e-15:
+                alpha = self.attn_dropout(alpha)
+            output = graph.send_ue_recv(feature, alpha, "mul", "sum")
         if self.concat:
             output = output.reshape(-1, self.num_heads * self.hidden_size)
         else:

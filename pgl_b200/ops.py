@@ -1006,6 +1006,79 @@ def gat_fused(csr, f, attn_src, attn_dst, negative_slope=0.2):
     return out.reshape(n_dst, H, Dh)
 
 
+class _GatFused(torch.autograd.Function):
+    """The single-pass GAT aggregation under autograd (reference pgl/nn/conv.py:333-339 differentiated by Paddle over
+    four ops).  Forward = pglb_gat_fused_train_csr_f32 (one launch; keeps only lse[N, H]).  Backward = one edge kernel
+    (pglb_gat_bwd_edge_f32: alpha rebuilt, SDDMM dot, softmax and LeakyReLU backward) + three reverse-CSR aggregations
+    on the existing kernels."""
+
+    @staticmethod
+    def forward(ctx, f2, a_s, a_d, fwd, bwd, slope, H, Dh):
+        n = int(f2.shape[0])
+        E = int(fwd["cols"].shape[0])
+        n_dst = int(fwd["indptr"].shape[0]) - 1
+        out = torch.empty((n_dst, H * Dh), dtype=torch.float32, device=f2.device)
+        lse = torch.zeros((n_dst, H), dtype=torch.float32, device=f2.device)
+        need = ctypes.c_size_t(0)
+        check(lib.pglb_spmm_csr_ws(n_dst, E, H * Dh, ctypes.byref(need)))
+        ws = workspace(f2.device, need.value)
+        with torch.cuda.device(f2.device):
+            check(lib.pglb_gat_fused_train_csr_f32(_ptr(fwd["indptr"]), _ptr(fwd["cols"]), _ptr(f2), f2.stride(0),
+                                                   _ptr(a_s), _ptr(a_d), float(slope), _ptr(out), out.stride(0),
+                                                   _ptr(lse), n_dst, n, E, H, Dh, _ptr(ws), ws.numel(), _stream()))
+        ctx.meta = (fwd, bwd, float(slope), H, Dh)
+        ctx.save_for_backward(f2, a_s, a_d, out, lse)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        fwd, bwd, slope, H, Dh = ctx.meta
+        bwd = bwd() if callable(bwd) else bwd
+        f2, a_s, a_d, out, lse = ctx.saved_tensors
+        g = _f32_2d(g)
+        E = int(fwd["cols"].shape[0])
+        n_src, n_dst = int(f2.shape[0]), int(out.shape[0])
+        alpha = torch.empty((E, H), dtype=torch.float32, device=g.device)
+        dz = torch.empty((E, H), dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            check(lib.pglb_gat_bwd_edge_f32(_ptr(fwd["rows"]), _ptr(fwd["cols"]), _ptr(fwd["eid"]), _ptr(f2),
+                                            f2.stride(0), _ptr(g), g.stride(0), _ptr(out), out.stride(0), _ptr(a_s),
+                                            _ptr(a_d), _ptr(lse), slope, E, H, Dh, _ptr(alpha), _ptr(dz), _stream()))
+        gf = gs = gd = None
+        if ctx.needs_input_grad[0]:   # grad f[s] = sum over the out-edges of s of alpha[e] * g[dst[e]]
+            gf = _spmm_raw(bwd["indptr"], bwd["cols"], g, n_src, "sum", eid=bwd["eid"], y2=alpha, y_bcast=BCAST_HEAD,
+                           head_dim=Dh, msg_op="mul", max_degree=bwd.get("max_degree", -1))
+        if ctx.needs_input_grad[1]:   # z = as[src] + ad[dst]: send_uv(add)'s backward
+            gs = _spmm_raw(bwd["indptr"], bwd["eid"], dz, n_src, "sum", max_degree=bwd.get("max_degree", -1))
+        if ctx.needs_input_grad[2]:
+            gd = _spmm_raw(fwd["indptr"], fwd["eid"], dz, n_dst, "sum", max_degree=fwd.get("max_degree", -1))
+        return gf, gs, gd, None, None, None, None, None
+
+
+GAT_FUSED_TRAIN = os.environ.get("PGLB_GAT_FUSED_TRAIN", "1") != "0"
+
+
+def gat_fused_train(fwd, bwd, f, attn_src, attn_dst, negative_slope=0.2):
+    """gat_fused with a backward (float32 only).  f [N, H, Dh], 64 < H*Dh <= 128, H % 4 == 0, Dh a power of two >= 4,
+    0 <= slope <= 1; returns [N, H, Dh], or None when the shape is outside the fused kernels (the caller keeps the
+    op-by-op path).  ``bwd`` is the reverse CSR dict or a callable returning it."""
+    require_cuda(f, attn_src, attn_dst)
+    n, H, Dh = int(f.shape[0]), int(f.shape[1]), int(f.shape[2])
+    if not GAT_FUSED_TRAIN or f.dtype != torch.float32 or H * Dh > 128 or H * Dh <= 64 or H % 4 or H > 32:
+        return None
+    if Dh < 4 or (Dh & (Dh - 1)) or not (0.0 <= float(negative_slope) <= 1.0):
+        return None
+    n_dst = int(fwd["indptr"].shape[0]) - 1
+    if n_dst != n or int(fwd["cols"].shape[0]) == 0 or fwd.get("rows") is None:
+        return None
+    f2 = _f32_2d(f)
+    a_s, a_d = _f32_2d(attn_src), _f32_2d(attn_dst)
+    if f2.data_ptr() % 16 or (f2.stride(0) * 4) % 16 or a_s.data_ptr() % 16:
+        return None
+    out = _GatFused.apply(f2, a_s, a_d, fwd, bwd, float(negative_slope), H, Dh)
+    return out.reshape(n_dst, H, Dh)
+
+
 @f64_through
 def aggregate_ue_slots(x, y_slots, fwd, n_dst, message_op="mul", reduce_op="sum"):
     """send_ue_recv whose edge operand is already in CSR slot order (read sequentially)."""

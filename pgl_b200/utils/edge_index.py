@@ -148,7 +148,7 @@ class EdgeIndex(object):
 
     def csr(self):
         """dict consumed by pgl_b200.ops: rows keyed by u, columns = v, eid per slot."""
-        return {"indptr": self._indptr, "cols": self._sorted_v, "eid": self._sorted_eid,
+        return {"indptr": self._indptr, "cols": self._sorted_v, "eid": self._sorted_eid, "rows": self._sorted_u,
                 "degree": self._degree, "max_degree": self.max_degree, "packed": self.packed_cols,
                 "plan": self.narrow_plan, "slot_scale": self.slot_scale}
 

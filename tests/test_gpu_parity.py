@@ -504,7 +504,13 @@ def test_gat_fused_inference_matches_unfused(pgl):
         conv.linear.weight.copy_(dev(w)); conv.linear.bias.copy_(dev(b))
         conv.weight_src.copy_(dev(wsrc)); conv.weight_dst.copy_(dev(wdst))
         fused = conv(g, dev(x)).cpu().numpy()
-    unfused = conv(g, dev(x)).detach().cpu().numpy()  # grad enabled -> op-by-op path
+    pgl.ops.GAT_FUSED_TRAIN = False   # grad enabled and the fused training path off -> op-by-op path
+    try:
+        unfused = conv(g, dev(x)).detach().cpu().numpy()
+    finally:
+        pgl.ops.GAT_FUSED_TRAIN = True
+    trained = conv(g, dev(x)).detach().cpu().numpy()  # grad enabled -> fused training path (same kernel + lse)
+    assert rel_err(trained, want) <= RTOL
     want = O.gat_conv(edges, n, x, w, b, wsrc, wdst, H, Dh, concat=True)
     assert rel_err(fused, want) <= RTOL
     assert rel_err(unfused, want) <= RTOL
