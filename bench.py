@@ -1030,6 +1030,7 @@ def bench_gat(args, torch, pgl, ops, GF, dev):
                 parity = gat_parity(torch, edges, n, f, a_s, a_d, step(), H, Dh)
             except Exception as ex:
                 parity = {"pass": None, "error": repr(ex)[:300]}
+    training = gat_training_leg(torch, pgl, ops, GF, g, f, a_s, a_d, H, Dh)
     ms_step = total_ms / args.steps
     kern_ms = float(np.mean(per))
     # per edge 8 + 32 + 512 + 32 (alpha write, training only) ; per node 32 + 512 + 8.
@@ -1045,14 +1046,62 @@ def bench_gat(args, torch, pgl, ops, GF, dev):
                    "max_in_degree": int(csr["max_degree"]), "l2": "features (0.5 GB) larger than L2"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs,
                      "traffic": read_traffic("gat_fused_bytes_per_launch"), "peak_source": peak_src,
-                     "algorithmic_bytes": b_alg, "kernel": "spmm_stream128_kernel<YM=2> (fused GAT)",
+                     "algorithmic_bytes": b_alg, "kernel": "spmm_gat5_kernel (fused GAT, TMA gather4)",
                      "kernel_ms_mean": kern_ms,
                      "note": "SURVEY 8d cfg3 model without the alpha write (inference): E*552 + N*552 bytes; with the "
                              "training-time alpha write the model is 6.42 GB"},
         "parity": parity, "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
         "full_layer": {"ms": layer_ms, "value": e / (layer_ms * 1e-3), "unit": "edges/s",
                        "what": "GATConv.forward (linear + attention logits + fused aggregation)"},
+        "training": training,
     }
+
+
+def gat_training_leg(torch, pgl, ops, GF, g, f, a_s, a_d, H, Dh, iters=5):
+    """Forward + backward of the attention + aggregation part of GATConv under autograd: the fused path
+    (ops._GatFused: single-pass forward keeping lse, backward edge kernel + reverse-CSR aggregations) next to the
+    op-by-op path (send_uv, LeakyReLU, edge_softmax, send_ue_recv, each with its own backward), and the largest
+    relative difference between their gradients at full size."""
+    try:
+        go = gen_features(torch, f.shape[0], H * Dh, 7, f.device).reshape(-1, H, Dh)
+        res = {}
+        grads = {}
+        for name in ("fused", "op_by_op"):
+            fa, sa, da = [t.detach().clone().requires_grad_(True) for t in (f, a_s, a_d)]
+
+            def one():
+                for t in (fa, sa, da):
+                    t.grad = None
+                if name == "fused":
+                    out = ops.gat_fused_train(g._fwd_csr(), g._bwd_csr, fa, sa, da, 0.2)
+                else:
+                    al = g.send_uv(sa, da, "add")
+                    al = torch.nn.functional.leaky_relu(al, 0.2)
+                    al = GF.edge_softmax(g, al)
+                    out = g.send_ue_recv(fa, al.reshape(-1, H, 1), "mul", "sum")
+                out.backward(go)
+
+            with torch.enable_grad():
+                one()
+                one()
+                torch.cuda.synchronize()
+                e0, e1 = _ev(torch), _ev(torch)
+                e0.record()
+                for _ in range(iters):
+                    one()
+                e1.record()
+                torch.cuda.synchronize()
+            res[name + "_fwd_bwd_ms"] = e0.elapsed_time(e1) / iters
+            grads[name] = [t.grad.detach().clone() for t in (fa, sa, da)]
+
+        def rel(a, b):
+            return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+        res["grad_max_rel_diff"] = {k: rel(a, b) for k, a, b in zip(("f", "attn_src", "attn_dst"), grads["fused"],
+                                                                     grads["op_by_op"])}
+        res["pass"] = all(v <= 5e-4 for v in res["grad_max_rel_diff"].values())
+        return res
+    except Exception as ex:   # never lose the timing line to the extra leg
+        return {"pass": None, "error": repr(ex)[:300]}
 
 
 def gat_parity(torch, edges, n, f, a_s, a_d, got, H, Dh, rows=4096):

@@ -276,7 +276,7 @@ int pglb_linear_tf32x3_f32(const float *x, int64_t ldx, const float *w, const fl
  * Neighbour sampling + reindex for mini-batch GraphSAGE.  Replace
  * paddle.geometric.sample_neighbors / reindex_graph as called by NeighborSampler.sample_neighbors
  * (pgl/sampling/sage.py:130-155) on the cached dst-CSR (row = adj_dst_index._sorted_v,
- * colptr = adj_dst_index._indptr).  EXPERIMENTAL: not yet validated on hardware (round 1).
+ * colptr = adj_dst_index._indptr).  Validated on hardware in round 2 (tests/test_gpu_sampling.py).
  * ---------------------------------------------------------------------------------- */
 /* count[i] = min(deg(nodes[i]), sample_size)  (all neighbours when sample_size < 0);
  * offsets[0..n] = exclusive scan of count, offsets[n] = total (n + 1 entries). */
@@ -330,6 +330,41 @@ int pglb_ipc_alloc(size_t bytes, void **dev_ptr, void *handle64);
 int pglb_ipc_free(void *dev_ptr);
 int pglb_ipc_open(const void *handle64, void **peer_ptr);
 int pglb_ipc_close(void *peer_ptr);
+
+/* ------------------------------------------------------------------------------------
+ * Partition -> local-graph pipeline on the device (csrc/localgraph.cu).
+ * ---------------------------------------------------------------------------------- */
+/* graph_kernel.map_nodes(nodes, reindex) (pgl/graph_kernel.pyx:123-138) with the dict as a dense table
+ * new_id[old_id] (table_size entries): out[i] = table[nodes[i]].  An id outside [0, table_size) gives -1 and
+ * sets *bad_flag (device int, may be NULL; the caller zeroes it) -- the reference's unordered_map would
+ * silently insert 0. */
+int pglb_map_nodes(const int64_t *nodes, int64_t n, const int64_t *table, int64_t table_size,
+                   int64_t *out, int32_t *bad_flag, void *stream);
+/* graph_kernel.map_edges(eid, edges, reindex) (pgl/graph_kernel.pyx:104-120): out[i, :] = table[edges[eid[i], :]];
+ * eid NULL = all edges in order.  edges / out contiguous [*, 2] int64. */
+int pglb_map_edges(const int64_t *eid, int64_t n, const int64_t *edges, int64_t num_edges,
+                   const int64_t *table, int64_t table_size, int64_t *out, int32_t *bad_flag, void *stream);
+/* inverse[perm[j]] = j.  With perm = sorted_eid of pglb_csr_build(u = part) -- the stable sort of the nodes by
+ * part -- inverse is the `new id of every node` of apps/GNNAutoScale/graph_partition.py:94-101 and the build's
+ * indptr is its offsets array. */
+int pglb_invert_perm(const int64_t *perm, int64_t n, int64_t *inverse, void *stream);
+/* One rank's local graph of a 1-D node partition whose parts are contiguous id ranges (this rank owns
+ * [lo, hi)).  Two calls, because the output sizes are data dependent:
+ *   count: counts[0] = E_local (edges whose destination is owned), counts[1] = H (distinct remote sources);
+ *          *bad_flag (device int, zeroed by the caller) is set when an endpoint lies outside [0, num_nodes).
+ *   fill : eid[E_local]       ascending global edge ids of the local edges,
+ *          dst_local[E_local] destination - lo,
+ *          col_local[E_local] source - lo when owned, else (hi - lo) + position of the source in halo_ids,
+ *          halo_ids[H]        ascending distinct remote source ids (= grouped by owner),
+ *          recv_counts[K]     how many of them lie in [offsets[p], offsets[p+1])  (offsets: device, K + 1 entries).
+ * The same workspace (pglb_halo_plan_ws bytes, 256-byte aligned) must be passed to both calls, untouched between. */
+int pglb_halo_plan_ws(int64_t num_edges, int64_t num_nodes, size_t *ws_bytes);
+int pglb_halo_plan_count(const int64_t *edges, int64_t num_edges, int64_t num_nodes, int64_t lo, int64_t hi,
+                         int64_t *counts, int32_t *bad_flag, void *ws, size_t ws_bytes, void *stream);
+int pglb_halo_plan_fill(const int64_t *edges, int64_t num_edges, int64_t num_nodes, int64_t lo, int64_t hi,
+                        const int64_t *offsets, int64_t num_parts, int64_t *eid, int64_t *dst_local,
+                        int64_t *col_local, int64_t *halo_ids, int64_t *recv_counts, void *ws, size_t ws_bytes,
+                        void *stream);
 
 /* ------------------------------------------------------------------------------------
  * Host: METIS K-way behind the same call shape as graph_kernel.metis_partition

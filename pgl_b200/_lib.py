@@ -82,6 +82,12 @@ _SIGS = {
     "pglb_sddmm_dot_f32": (c_int, [_p, _p, _p, _i64, _p, _i64, _i64, _i64, _i64, _p, _p]),
     "pglb_edge_softmax_bwd_csr_f32": (c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _p]),
     "pglb_maxmin_bwd_f32": (c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _p]),
+    "pglb_map_nodes": (c_int, [_p, _i64, _p, _i64, _p, _p, _p]),
+    "pglb_map_edges": (c_int, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _p]),
+    "pglb_invert_perm": (c_int, [_p, _i64, _p, _p]),
+    "pglb_halo_plan_ws": (c_int, [_i64, _i64, POINTER(c_size_t)]),
+    "pglb_halo_plan_count": (c_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _p, c_size_t, _p]),
+    "pglb_halo_plan_fill": (c_int, [_p, _i64, _i64, _i64, _i64, _p, _i64, _p, _p, _p, _p, _p, _p, c_size_t, _p]),
     "pglb_metis_partition": (c_int, [c_char_p, _i64, _p, _p, _i64, _p, _p, c_int, _p]),
 }
 

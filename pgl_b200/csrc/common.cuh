@@ -68,6 +68,10 @@ inline cudaError_t ensure_dyn_smem(K kernel, int bytes, std::atomic<unsigned lon
     return e;
 }
 
+// multi-block int64 prefix sum (csr_build.cu): in and out may alias, tmp holds scan_i64_ws_bytes(n) bytes
+size_t scan_i64_ws_bytes(int64_t n);
+int scan_i64(const int64_t *in, int64_t *out, int64_t n, int inclusive, void *tmp, cudaStream_t stream);
+
 // ---- device helpers -------------------------------------------------------------------
 
 // streaming (evict-first) loads for index data that is read exactly once

@@ -114,9 +114,10 @@ __global__ void __launch_bounds__(SCAN_T) scan_apply_kernel(const int64_t *__res
 
 static inline int64_t scan_blocks(int64_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
 static inline size_t scan_ws_bytes(int64_t n) { return align_up(sizeof(int64_t) * (size_t)std::max<int64_t>(scan_blocks(n), 1), 256); }
+size_t scan_i64_ws_bytes(int64_t n) { return scan_ws_bytes(n); }
 
-// in and out may alias.  tmp: scan_ws_bytes(n).
-static int scan_i64(const int64_t *in, int64_t *out, int64_t n, int inclusive, void *tmp,
+// in and out may alias.  tmp: scan_ws_bytes(n).  (also used by localgraph.cu)
+int scan_i64(const int64_t *in, int64_t *out, int64_t n, int inclusive, void *tmp,
                     cudaStream_t stream) {
     if (n <= 0) return PGLB_OK;
     const int64_t nb = scan_blocks(n);

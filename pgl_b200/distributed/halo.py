@@ -1,7 +1,9 @@
 """HaloPlan: which rows a rank owns, which remote rows it needs, and how they move.
 
-Pure torch index arithmetic on whatever device the edge tensor lives on, plus
-``torch.distributed`` collectives (NCCL on GPUs, gloo in the CPU tests).  No feature math.
+On CUDA tensors the plan is built by the kernels of csrc/localgraph.cu (``ops.halo_plan``: flag arrays + prefix
+sums, no sort, no hash; ``ops.partition_relabel`` / ``ops.map_edges`` for the relabelling); on CPU tensors (the gloo
+tests of the host logic) by the torch index arithmetic below, which the GPU tests hold the kernels against bit for bit.
+``torch.distributed`` collectives (NCCL on GPUs, gloo in the CPU tests) move counts and id lists.  No feature math.
 """
 import numpy as np
 import torch
@@ -45,7 +47,7 @@ class HaloPlan(object):
         pass
 
     @classmethod
-    def build(cls, edges, num_nodes, offsets, rank, world, group=None):
+    def build(cls, edges, num_nodes, offsets, rank, world, group=None, force_torch=False):
         self = cls()
         self.rank, self.world, self.group = int(rank), int(world), group
         self.offsets = [int(o) for o in offsets]
@@ -53,21 +55,28 @@ class HaloPlan(object):
         self.lo, self.hi = lo, hi
         self.n_local = hi - lo
         dev = edges.device
-        src_all, dst_all = edges[:, 0], edges[:, 1]
-        mine = (dst_all >= lo) & (dst_all < hi)
-        eid = torch.nonzero(mine, as_tuple=False).reshape(-1)
-        src = src_all.index_select(0, eid)
-        self.eid = eid
-        self.dst_local = dst_all.index_select(0, eid) - lo
-        remote = (src < lo) | (src >= hi)
-        halo_ids = torch.unique(src[remote])  # sorted => grouped by owner
-        self.halo_ids = halo_ids
-        self.n_halo = int(halo_ids.shape[0])
-        pos = torch.searchsorted(halo_ids, src) if self.n_halo else torch.zeros_like(src)
-        self.col_local = torch.where(remote, pos + self.n_local, src - lo)
-        off_t = torch.tensor(self.offsets, dtype=torch.int64, device=dev)
-        bounds = torch.searchsorted(halo_ids, off_t) if self.n_halo else torch.zeros_like(off_t)
-        recv_counts = (bounds[1:] - bounds[:-1]).to(torch.int64)
+        if edges.is_cuda and not force_torch:
+            from .. import ops
+            self.eid, self.dst_local, self.col_local, halo_ids, recv_counts = ops.halo_plan(
+                edges, num_nodes, lo, hi, self.offsets)
+            self.halo_ids = halo_ids
+            self.n_halo = int(halo_ids.shape[0])
+        else:
+            src_all, dst_all = edges[:, 0], edges[:, 1]
+            mine = (dst_all >= lo) & (dst_all < hi)
+            eid = torch.nonzero(mine, as_tuple=False).reshape(-1)
+            src = src_all.index_select(0, eid)
+            self.eid = eid
+            self.dst_local = dst_all.index_select(0, eid) - lo
+            remote = (src < lo) | (src >= hi)
+            halo_ids = torch.unique(src[remote])  # sorted => grouped by owner
+            self.halo_ids = halo_ids
+            self.n_halo = int(halo_ids.shape[0])
+            pos = torch.searchsorted(halo_ids, src) if self.n_halo else torch.zeros_like(src)
+            self.col_local = torch.where(remote, pos + self.n_local, src - lo)
+            off_t = torch.tensor(self.offsets, dtype=torch.int64, device=dev)
+            bounds = torch.searchsorted(halo_ids, off_t) if self.n_halo else torch.zeros_like(off_t)
+            recv_counts = (bounds[1:] - bounds[:-1]).to(torch.int64)
         send_counts = torch.empty_like(recv_counts)
         if world > 1:
             dist.all_to_all_single(send_counts, recv_counts, group=group)

@@ -77,9 +77,15 @@ class ShardedGraph(object):
                 dist.broadcast(part_t, 0, group=group)
             part = part_t.cpu().numpy()
         if part is not None:
-            new_id, offsets = relabel_by_partition(part, world)
-            nid = torch.from_numpy(new_id).to(edges.device)
-            edges = nid[edges]
+            if edges.is_cuda:   # stable sort by part + inverse permutation + edge relabel: csrc/localgraph.cu
+                nid, off_t = ops.partition_relabel(torch.as_tensor(np.asarray(part), dtype=torch.int64).to(edges.device),
+                                                   world)
+                new_id, offsets = nid.cpu().numpy(), [int(v) for v in off_t.tolist()]
+                edges = ops.map_edges(None, edges, nid)
+            else:
+                new_id, offsets = relabel_by_partition(part, world)
+                nid = torch.from_numpy(new_id).to(edges.device)
+                edges = nid[edges]
         else:
             offsets = block_offsets(n, world)
         plan = HaloPlan.build(edges, n, offsets, rank, world, group=group)

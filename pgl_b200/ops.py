@@ -136,6 +136,92 @@ def csr_build(u, v, num_nodes):
     return degree, sv, su, se, indptr
 
 
+# partition -> local graph (csrc/localgraph.cu)
+# ------------------------------------------------------------------------------------------
+
+
+def map_nodes(nodes, table, strict=True):
+    """graph_kernel.map_nodes on the device: table[nodes] for a dense table new_id[old_id] (int64 CUDA tensors).
+    strict: ids outside the table raise (one 4-byte read back); otherwise they map to -1."""
+    require_cuda(nodes, table)
+    nodes = _i64(nodes).contiguous()
+    table = _i64(table).contiguous()
+    out = torch.empty_like(nodes)
+    bad = torch.zeros(1, dtype=torch.int32, device=nodes.device)
+    with torch.cuda.device(nodes.device):
+        check(lib.pglb_map_nodes(_ptr(nodes), nodes.numel(), _ptr(table), table.numel(), _ptr(out), _ptr(bad),
+                                 _stream()))
+    if strict and int(bad.item()):
+        raise IndexError("pgl_b200.map_nodes: node id outside the relabelling table")
+    return out
+
+
+def map_edges(eid, edges, table, strict=True):
+    """graph_kernel.map_edges on the device: table[edges[eid]] (eid None = every edge in order)."""
+    require_cuda(edges, table)
+    edges = _i64(edges).contiguous()
+    table = _i64(table).contiguous()
+    if edges.dim() != 2 or edges.shape[1] != 2:
+        raise ValueError("pgl_b200.map_edges: edges must be [E, 2]")
+    if eid is not None:
+        eid = _i64(eid).contiguous()
+    n = int(eid.numel()) if eid is not None else int(edges.shape[0])
+    out = torch.empty((n, 2), dtype=torch.int64, device=edges.device)
+    bad = torch.zeros(1, dtype=torch.int32, device=edges.device)
+    with torch.cuda.device(edges.device):
+        check(lib.pglb_map_edges(_ptr(eid), n, _ptr(edges), int(edges.shape[0]), _ptr(table), table.numel(),
+                                 _ptr(out), _ptr(bad), _stream()))
+    if strict and int(bad.item()):
+        raise IndexError("pgl_b200.map_edges: edge or node id outside its table")
+    return out
+
+
+def partition_relabel(part, num_parts):
+    """part[N] (int64 CUDA tensor, values in [0, num_parts)) -> (new_id[N], offsets[num_parts + 1]) such that every
+    part is a contiguous range of new ids, stable inside a part (reference apps/GNNAutoScale/graph_partition.py:94-101:
+    ``permutation = argsort(part)`` + offsets).  The stable sort is pglb_csr_build's radix sort with u = part."""
+    require_cuda(part)
+    part = _i64(part).contiguous()
+    n = int(part.numel())
+    deg, sv, su, perm, offsets = csr_build(part, part, int(num_parts))
+    new_id = torch.empty(n, dtype=torch.int64, device=part.device)
+    with torch.cuda.device(part.device):
+        check(lib.pglb_invert_perm(_ptr(perm), n, _ptr(new_id), _stream()))
+    return new_id, offsets
+
+
+def halo_plan(edges, num_nodes, lo, hi, offsets):
+    """One rank's local graph of a contiguous 1-D node partition (pglb_halo_plan_count / _fill).
+    edges [E, 2] int64 CUDA (global ids), this rank owns [lo, hi), offsets = python list / tensor of K + 1 part
+    starts.  Returns (eid, dst_local, col_local, halo_ids, recv_counts) -- all int64 CUDA tensors."""
+    require_cuda(edges)
+    edges = _i64(edges).contiguous()
+    dev = edges.device
+    E, N = int(edges.shape[0]), int(num_nodes)
+    off_t = torch.as_tensor(offsets, dtype=torch.int64).to(dev).contiguous()
+    K = int(off_t.numel()) - 1
+    need = ctypes.c_size_t(0)
+    check(lib.pglb_halo_plan_ws(E, N, ctypes.byref(need)))
+    ws = torch.empty(max(need.value, 1), dtype=torch.uint8, device=dev)  # private: must survive between the two calls
+    counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.pglb_halo_plan_count(_ptr(edges), E, N, int(lo), int(hi), _ptr(counts), _ptr(bad), _ptr(ws),
+                                       ws.numel(), _stream()))
+        e_loc, n_halo = (int(v) for v in counts.tolist())
+        if int(bad.item()):
+            raise IndexError("pgl_b200.halo_plan: edge endpoint outside [0, num_nodes)")
+        eid = torch.empty(e_loc, dtype=torch.int64, device=dev)
+        dst_local = torch.empty(e_loc, dtype=torch.int64, device=dev)
+        col_local = torch.empty(e_loc, dtype=torch.int64, device=dev)
+        halo_ids = torch.empty(n_halo, dtype=torch.int64, device=dev)
+        recv_counts = torch.zeros(K, dtype=torch.int64, device=dev)
+        check(lib.pglb_halo_plan_fill(_ptr(edges), E, N, int(lo), int(hi), _ptr(off_t), K, _ptr(eid),
+                                      _ptr(dst_local), _ptr(col_local), _ptr(halo_ids), _ptr(recv_counts), _ptr(ws),
+                                      ws.numel(), _stream()))
+    return eid, dst_local, col_local, halo_ids, recv_counts
+
+
 def segment_ids_from_indptr(indptr, num_edges):
     """(uniq_ind, segment_ids) of a CSR == paddle.unique(sorted_key, return_inverse=True)
     (reference pgl/utils/helper.py:156-160).  One D2H read of K (the reference's unique syncs too)."""
