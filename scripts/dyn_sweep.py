@@ -1,0 +1,106 @@
+"""Static block -> task map vs the device-side task queue (PGLB_V5_DYN / PGLB_GAT_DYN = 0 / 1 / 2) on cfg5 (one GPU
+and ONE rank's shard of the 8 x 1 grid) and on cfg3's fused GAT aggregation.  The mode is read per call by the
+library, so one process times all of them on the same graph.  Prints one JSON line per case."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import pgl_b200 as pgl  # noqa: E402
+from pgl_b200 import ops  # noqa: E402
+
+
+def time_steps(step, steps=20, warm=5):
+    for _ in range(warm):
+        step()
+    torch.cuda.synchronize()
+    per = []
+    for _ in range(steps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step()
+        b.record()
+        torch.cuda.synchronize()
+        per.append(a.elapsed_time(b))
+    return float(np.mean(per)), float(np.min(per))
+
+
+def gcn_case(dev, n, e, d, rr, r, label):
+    edges = bench.gen_edges(torch, n, e, 0.8, 20240922, dev)
+    indeg = torch.bincount(edges[:, 1], minlength=n)
+    bounds = bench.balanced_row_bounds(torch, indeg, rr)
+    lo, hi = bounds[r], bounds[r + 1]
+    n_loc = hi - lo
+    norm = ops.degree_norm(indeg).reshape(-1)
+    if rr > 1:
+        m = (edges[:, 1] >= lo) & (edges[:, 1] < hi)
+        edges = torch.stack([edges[m, 0], edges[m, 1] - lo], 1)
+    e_loc = int(edges.shape[0])
+    g = pgl.Graph(edges=edges, num_nodes=n)
+    fwd = g._csr_for_rows(n_loc)
+    norm_dst = norm[lo:hi].contiguous()
+    x = bench.gen_features(torch, n, d, 20240923, dev)
+    out = torch.empty(n_loc, d, device=dev)
+    packed = ops._packed_of(fwd, x)
+
+    def step():
+        return ops._spmm_raw(fwd["indptr"], fwd["cols"], x, n_loc, "sum", scale_src=norm, scale_dst=norm_dst,
+                             max_degree=fwd["max_degree"], out=out, packed=packed)
+
+    base = None
+    for mode in (0, 1, 2, 0):
+        os.environ["PGLB_V5_DYN"] = str(mode)
+        mean, best = time_steps(step)
+        got = step().clone()
+        if base is None:
+            base = got
+        b_alg = bench.algorithmic_bytes(n_loc, e_loc, d)
+        print(json.dumps({"case": label, "dyn": mode, "ms_mean": mean, "ms_min": best, "edges": e_loc, "rows": n_loc,
+                          "frac_of_6582": b_alg / (mean * 1e-3) / 1e9 / 6582.5, "bit_identical": bool(torch.equal(got, base))}),
+              flush=True)
+    os.environ.pop("PGLB_V5_DYN", None)
+    del g, fwd, x, out, edges
+    torch.cuda.empty_cache()
+
+
+def gat_case(dev):
+    n, e, H, Dh = 1 << 20, 10_000_000, 8, 16
+    edges = bench.rmat_edges(torch, 20, e, seed=1, device=dev)
+    g = pgl.Graph(edges=edges, num_nodes=n)
+    x = bench.gen_features(torch, n, 128, 2, dev)
+    torch.manual_seed(3)
+    conv = pgl.nn.GATConv(128, Dh, feat_drop=0, attn_drop=0, num_heads=H).to(dev).eval()
+    csr = g._fwd_csr()
+    with torch.no_grad():
+        f = (x @ conv.linear.weight + conv.linear.bias).reshape(-1, H, Dh).contiguous()
+        a_s = (f * conv.weight_src).sum(-1).contiguous()
+        a_d = (f * conv.weight_dst).sum(-1).contiguous()
+        base = None
+        for mode in (0, 1, 2, 0):
+            os.environ["PGLB_GAT_DYN"] = str(mode)
+            mean, best = time_steps(lambda: ops.gat_fused(csr, f, a_s, a_d, 0.2))
+            got = ops.gat_fused(csr, f, a_s, a_d, 0.2).clone()
+            if base is None:
+                base = got
+            b_alg = e * (8 + 32 + 512) + n * (32 + 512 + 8)
+            print(json.dumps({"case": "cfg3 fused GAT", "dyn": mode, "ms_mean": mean, "ms_min": best,
+                              "frac_of_6582": b_alg / (mean * 1e-3) / 1e9 / 6582.5,
+                              "bit_identical": bool(torch.equal(got, base))}), flush=True)
+    os.environ.pop("PGLB_GAT_DYN", None)
+
+
+if __name__ == "__main__":
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    what = sys.argv[1:] or ["gat", "shard", "full"]
+    if "gat" in what:
+        gat_case(dev)
+    if "shard" in what:
+        gcn_case(dev, 10_000_000, 100_000_000, 128, 8, 2, "cfg5 rank 2 of the 8 x 1 grid")
+    if "full" in what:
+        gcn_case(dev, 10_000_000, 100_000_000, 128, 1, 0, "cfg5 one GPU")
