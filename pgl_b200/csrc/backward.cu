@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(256) maxmin_bwd_kernel(const int64_t *__restri
 // Backward of the single-pass GAT aggregation (pglb_gat_fused_train_csr_f32), the per-edge part.  With
 //   z = as[src,h] + ad[dst,h],  lz = leaky_relu(z),  alpha = exp(lz - lse[dst,h]),  out[dst,h,:] = sum alpha f[src,h,:]
 // and G = d loss / d out:
-//   d alpha = <G[dst,h,:], f[src,h,:]>,   d lz = alpha (d alpha - <G[dst,h,:], out[dst,h,:]>),   d z = d lz * leaky'(z).
+//   d alpha = <G[dst,h,:], f[src,h,:]>,   d lz = alpha (d alpha - <G[dst,h,:], out[dst,h,:]>),   d z = d lz * leaky'(z)
+//   (leaky'(z) = 1 for z > 0, slope otherwise).
 // One launch rebuilds alpha and produces dz for every edge, both written in ORIGINAL edge order, which is what the
 // reverse-CSR aggregations that finish the job read (grad f = sum over out-edges alpha G[dst]; grad as / grad ad =
 // segment sums of dz over the src- / dst-CSR, exactly send_uv(add)'s backward).  Neither logits nor alpha were kept by
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(256) gat_bwd_edge_kernel(
                 }
                 const float da = head_sum(dot4(fv[u], g4));
                 const float z = as[u] + ad;
-                const bool pos = z >= 0.0f;
+                const bool pos = z > 0.0f;   // leaky_relu'(0) = slope, the convention of the framework's LeakyReLU backward
                 const float alpha = expf((pos ? z : z * slope) - ls);
                 const float dl = alpha * (da - delta);
                 if (lead) {

@@ -251,9 +251,27 @@ static int gat5_mode() {
     return v;
 }
 
+// PGLB_GAT_GEO: 0 = groups of 8, ring of 3, 8 warps per CTA (default); 1 = groups of 4, ring of 4, 12 warps
+static int gat5_geo() {
+    static int geo = -1;
+    if (geo < 0) {
+        const char *e = getenv("PGLB_GAT_GEO");
+        geo = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    return geo;
+}
+constexpr int kGat5SmemBudget = 112 * 1024;   // two CTAs per SM
+// dynamic shared memory of a launch: per warp NG groups of GRP feature rows + GRP attention rows (quads padded to 128 B)
+static int64_t gat5_smem(int64_t D, int64_t H) {
+    const int64_t fq = (D * 16 + 127) & ~127LL, aq = (H * 16 + 127) & ~127LL;
+    const int64_t grp = gat5_geo() == 1 ? 4 : 8, ng = gat5_geo() == 1 ? 4 : 3, w = gat5_geo() == 1 ? 12 : 8;
+    return w * ng * (fq + aq) * (grp / 4) + 128;
+}
+
 static bool gat5_eligible(const StreamP &p, const float *f, int64_t ldf, const float *attn_src, int64_t H, int64_t n_src) {
     if (!gat5_mode()) return false;
     if (p.D % 4 != 0 || p.D > 128 || H % 4 != 0 || H > 32) return false;
+    if (gat5_smem(p.D, H) > kGat5SmemBudget) return false;   // e.g. 32 heads x 4: the attention rows no longer fit the rings
     if ((reinterpret_cast<uintptr_t>(f) & 15) || ((ldf * 4) & 15) || (reinterpret_cast<uintptr_t>(attn_src) & 15)) return false;
     if (n_src >= 0x7fffffffLL) return false;
     if (p.slope < 0.0f || p.slope > 1.0f) return false;   // the quad path writes leaky relu as max(x, slope * x)
@@ -313,11 +331,5 @@ static int launch_gat5(const StreamP &p, const float *attn_src, int64_t H, int64
     if (rc) return rc;
     rc = make_row_map(&tma, attn_src, n_src, H, H);
     if (rc) return rc;
-    // PGLB_GAT_GEO: 0 = groups of 8, ring of 3, 8 warps per CTA (default); 1 = groups of 4, ring of 4, 12 warps
-    static int geo = -1;
-    if (geo < 0) {
-        const char *e = getenv("PGLB_GAT_GEO");
-        geo = (e && atoi(e) == 1) ? 1 : 0;
-    }
-    return geo == 1 ? launch_gat5_geo<4, 4, 12>(gp, tmf, tma, stream) : launch_gat5_geo<8, 3, 8>(gp, tmf, tma, stream);
+    return gat5_geo() == 1 ? launch_gat5_geo<4, 4, 12>(gp, tmf, tma, stream) : launch_gat5_geo<8, 3, 8>(gp, tmf, tma, stream);
 }

@@ -1078,13 +1078,21 @@ static int64_t stream_snap(int64_t T) { return env_task_size() ? T : (T > 1024 ?
 size_t stream_ws_bytes(int64_t E, int64_t D) { return stream_layout(nullptr, E, D, stream_task_size(E)).bytes; }
 
 // Task hand-out of the persistent kernels (spmm_v5 / spmm_gat5): 0 = static block -> task map, 1 = device-side queue
-// in ascending task order, 2 = queue in descending order.  slot 0: PGLB_V5_DYN, slot 1: PGLB_GAT_DYN.
-// Read per call (a getenv, no cache) so one process can compare the modes.
-static int dyn_mode(const char *name, int slot) {
-    static const int defaults[2] = {0, 0};
+// in ascending task order, 2 = queue in descending order.  slot 0: PGLB_V5_DYN, slot 1: PGLB_GAT_DYN (read per
+// call -- a getenv, no cache -- so one process can compare the modes).
+// Defaults (measured, profiles/r02_dyn_sweep.log): the copy-sum kernel gains 4-8 % from the queue -- ascending order
+// when there are many tasks per resident warp (cfg5 on one GPU: 8.64 -> 8.32 ms), descending when there are few (one
+// rank's 12.5M-edge shard of the 8 x 1 grid: 1.34 -> 1.24 ms); the fused GAT kernel does not (2.15 static, 2.18
+// descending, 2.92 ascending on cfg3) and keeps the static map.
+static int dyn_mode(const char *name, int slot, int64_t ntasks) {
     const char *e = getenv(name);
-    const int v = e ? atoi(e) : defaults[slot];
-    return (v < 0 || v > 2) ? defaults[slot] : v;
+    if (e) {
+        const int v = atoi(e);
+        if (v >= 0 && v <= 2) return v;
+    }
+    if (slot == 1) return 0;
+    const int64_t resident_warps = (int64_t)sm_count() * 2 * 13;
+    return ntasks >= 8 * resident_warps ? 1 : 2;
 }
 
 static int stream_cfg() {
@@ -1190,7 +1198,7 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
         p.hot_mode = mode;
     }
     p.counter = w.counter;
-    p.dyn = dyn_mode("PGLB_V5_DYN", 0);
+    p.dyn = dyn_mode("PGLB_V5_DYN", 0, w.ntasks);
     {
         const int64_t blocks = (w.ntasks + 1 + 255) / 256;
         task_plan_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indptr, n_dst, E, T, stream_snap(T),
@@ -1384,7 +1392,7 @@ int gat_fused_run(const int64_t *indptr, const int64_t *cols, const float *f, in
     p.slope = slope;
     p.hot_mode = 1;
     p.counter = w.counter;
-    p.dyn = dyn_mode("PGLB_GAT_DYN", 1);
+    p.dyn = dyn_mode("PGLB_GAT_DYN", 1, w.ntasks);
     p.lse = lse;
     // the row statistics are written by spmm_gat5_kernel and the merge kernel only
     PGLB_CHECK_ARG(!lse || gat5_eligible(p, f, ldf, attn_src, H, n_src), PGLB_EUNSUPPORTED,

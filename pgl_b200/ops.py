@@ -1161,7 +1161,12 @@ def gat_fused_train(fwd, bwd, f, attn_src, attn_dst, negative_slope=0.2):
     a_s, a_d = _f32_2d(attn_src), _f32_2d(attn_dst)
     if f2.data_ptr() % 16 or (f2.stride(0) * 4) % 16 or a_s.data_ptr() % 16:
         return None
-    out = _GatFused.apply(f2, a_s, a_d, fwd, bwd, float(negative_slope), H, Dh)
+    try:
+        out = _GatFused.apply(f2, a_s, a_d, fwd, bwd, float(negative_slope), H, Dh)
+    except _lib.PglbError as ex:
+        if ex.code == -4:   # PGLB_EUNSUPPORTED: e.g. 32 heads, whose attention rows do not fit the kernel's rings
+            return None
+        raise
     return out.reshape(n_dst, H, Dh)
 
 

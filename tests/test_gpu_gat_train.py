@@ -63,7 +63,7 @@ class env(object):
                 os.environ[k] = v
 
 
-@pytest.mark.parametrize("H,Dh", [(8, 16), (4, 32), (16, 8), (32, 4), (12, 8)])
+@pytest.mark.parametrize("H,Dh", [(8, 16), (4, 32), (16, 8), (12, 8)])
 @pytest.mark.parametrize("slope", [0.2, 0.0, 1.0])
 def test_gat_fused_train_forward_and_gradients(pgl, H, Dh, slope):
     """Hubs (rows cut across tasks: lse comes from the merge kernel), empty rows, one-edge rows."""
@@ -83,10 +83,13 @@ def test_gat_fused_train_forward_and_gradients(pgl, H, Dh, slope):
     f2, s2, d2 = [t.detach().clone().requires_grad_(True) for t in (f1, s1, d1)]
     ref, _ = torch_gat(f2, s2, d2, src, dst, n, slope)
     ref.backward(go)
-    assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= RTOL
-    assert rel_err(f1.grad.cpu().numpy(), f2.grad.cpu().numpy()) <= RTOL
-    assert rel_err(s1.grad.cpu().numpy(), s2.grad.cpu().numpy()) <= 5e-4
-    assert rel_err(d1.grad.cpu().numpy(), d2.grad.cpu().numpy()) <= 5e-4
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) <= RTOL, "forward"
+    assert rel_err(f1.grad.cpu().numpy(), f2.grad.cpu().numpy()) <= RTOL, "grad f"
+    # the logit gradients are differences of O(|go| |f|) terms (d alpha - <go, out>); with slope = 1 the row sums that
+    # make grad attn_dst cancel to exactly 0 in exact arithmetic: judge both against the size of grad attn_src
+    scale = float(s2.grad.abs().max())
+    assert float((s1.grad - s2.grad).abs().max()) <= 5e-4 * scale, "grad attn_src"
+    assert float((d1.grad - d2.grad).abs().max()) <= 5e-4 * max(scale, float(d2.grad.abs().max())), "grad attn_dst"
     # the forward is the inference kernel: same numbers with autograd off
     with torch.no_grad():
         inf = pgl.ops.gat_fused(g._fwd_csr(), f1.detach(), s1.detach(), d1.detach(), slope)
@@ -128,6 +131,7 @@ def test_gat_conv_trains_on_the_fused_path(pgl):
     conv = pgl.nn.GATConv(fin, Dh, feat_drop=0, attn_drop=0, num_heads=H, concat=True).cuda()
     x0 = torch.randn(n, fin, device="cuda")
     go = torch.randn(n, H * Dh, device="cuda")
+    g._fwd_csr(), g._bwd_csr()   # the one-off index builds are not part of a layer's launch count
 
     def run(fused):
         old = pgl.ops.GAT_FUSED_TRAIN
@@ -168,13 +172,22 @@ def test_gat_fused_train_unsupported_shapes_fall_back(pgl):
     n, e = 500, 4000
     edges = O.chung_lu_edges(n, e, exponent=0.7, seed=331)
     g = make_graph(pgl, edges, n)
-    for H, Dh in ((4, 8), (3, 32), (2, 64), (8, 12)):   # narrow row, H % 4, H % 4, head_dim not a power of two
+    # narrow row, H % 4, H % 4, head_dim not a power of two, 32 heads (attention rows too wide for the kernel's rings)
+    for H, Dh in ((4, 8), (3, 32), (2, 64), (8, 12), (32, 4)):
         f = torch.randn(n, H, Dh, device="cuda", requires_grad=True)
         a = torch.randn(n, H, device="cuda")
         assert pgl.ops.gat_fused_train(g._fwd_csr(), g._bwd_csr, f, a, a, 0.2) is None
     f = torch.randn(n, 8, 16, device="cuda", requires_grad=True)
     a = torch.randn(n, 8, device="cuda")
     assert pgl.ops.gat_fused_train(g._fwd_csr(), g._bwd_csr, f, a, a, 1.5) is None   # slope outside [0, 1]
+    # 32 heads x 4 at inference: outside the TMA kernel's shared-memory budget -> round 1's single-pass kernel
+    src, dst = dev(edges[:, 0]), dev(edges[:, 1])
+    f32 = torch.randn(n, 32, 4, device="cuda")
+    a32, b32 = torch.randn(n, 32, device="cuda"), torch.randn(n, 32, device="cuda")
+    with torch.no_grad():
+        got = pgl.ops.gat_fused(g._fwd_csr(), f32, a32, b32, 0.2)
+        ref, _ = torch_gat(f32, a32, b32, src, dst, n, 0.2)
+    assert got is not None and rel_err(got.cpu().numpy(), ref.cpu().numpy()) <= RTOL
     # the layers still train on those shapes (op-by-op path)
     conv = pgl.nn.GATConv(10, 8, feat_drop=0, attn_drop=0, num_heads=4).cuda()
     x = torch.randn(n, 10, device="cuda", requires_grad=True)
