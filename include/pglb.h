@@ -331,6 +331,11 @@ int pglb_ipc_free(void *dev_ptr);
 int pglb_ipc_open(const void *handle64, void **peer_ptr);
 int pglb_ipc_close(void *peer_ptr);
 
+/* Debug aid (scripts/task_trace.py): while `buffer` (device, capacity_tasks x 4 int64) is armed, the wide-row
+ * aggregation kernels record (start ns, end ns, SM id, warp slot) for every task of a launch with at most
+ * capacity_tasks tasks.  buffer = NULL disarms.  Process-global; not for concurrent use. */
+int pglb_debug_task_trace(void *buffer, int64_t capacity_tasks);
+
 /* ------------------------------------------------------------------------------------
  * Partition -> local-graph pipeline on the device (csrc/localgraph.cu).
  * ---------------------------------------------------------------------------------- */

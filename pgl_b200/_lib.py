@@ -82,6 +82,7 @@ _SIGS = {
     "pglb_sddmm_dot_f32": (c_int, [_p, _p, _p, _i64, _p, _i64, _i64, _i64, _i64, _p, _p]),
     "pglb_edge_softmax_bwd_csr_f32": (c_int, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _p]),
     "pglb_maxmin_bwd_f32": (c_int, [_p, _p, _p, _p, _p, _p, _i64, _i64, _p]),
+    "pglb_debug_task_trace": (c_int, [_p, _i64]),
     "pglb_map_nodes": (c_int, [_p, _i64, _p, _i64, _p, _p, _p]),
     "pglb_map_edges": (c_int, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _p]),
     "pglb_invert_perm": (c_int, [_p, _i64, _p, _p]),

@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_gat5_kernel(const Gat5P gp, co
     } else {
         task = (lin * gp.task_mul) % p.ntasks;
     }
+    const long long t_task0 = p.trace ? global_ns() : 0;
     const int64_t a = ld_ro(p.start + task);
     const int64_t b = ld_ro(p.start + task + 1);
     const int cnt = (int)(b - a);
@@ -93,7 +94,11 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_gat5_kernel(const Gat5P gp, co
         bool head = beg_rel < 0;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         float m_run = -INFINITY, l_run = 0.0f;
-        float ad = act ? __ldg(p.attn_dst + row * p.ldy + yhead) : 0.0f;
+        // attn_dst of the current row and, prefetched, of the next one: a row of one or two slots ends before a
+        // dependent load issued at its start would be back
+        auto load_ad = [&](int64_t r) -> float { return (act && r < p.n_rows) ? __ldg(p.attn_dst + r * p.ldy + yhead) : 0.0f; };
+        float ad = load_ad(row);
+        float ad_nxt = load_ad(row + 1);
 
         auto finish_row = [&]() {
             if (head) {
@@ -116,21 +121,23 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_gat5_kernel(const Gat5P gp, co
             beg_rel = end_rel;
             end_rel = nxt_rel;
             nxt_rel = (row + 2 <= p.n_rows) ? rel(ld_ro(p.indptr + row + 2)) : (1 << 30);
+            ad = ad_nxt;
             if (end_rel == beg_rel && row < p.n_rows) {
                 const int64_t pos_abs = a + beg_rel;
                 if (pos_abs >= p.E) {
                     row = p.n_rows;
                     end_rel = 1 << 30;
                 } else {
-                    row = row_of_slot_cold(p.indptr, p.n_rows, pos_abs);
+                    row = row_of_slot_from(p.indptr, p.n_rows, row, pos_abs);
                     end_rel = rel(ld_ro(p.indptr + row + 1));
                     nxt_rel = (row + 2 <= p.n_rows) ? rel(ld_ro(p.indptr + row + 2)) : (1 << 30);
                 }
+                ad = load_ad(row);
             }
+            ad_nxt = load_ad(row + 1);
             acc = make_float4(0.f, 0.f, 0.f, 0.f);
             m_run = -INFINITY;
             l_run = 0.0f;
-            ad = (act && row < p.n_rows) ? __ldg(p.attn_dst + row * p.ldy + yhead) : 0.0f;
         };
 
         auto load_col = [&](int batch) -> unsigned {
@@ -237,6 +244,7 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_gat5_kernel(const Gat5P gp, co
         if (DYN) gtot += (unsigned)ngroups;
     }
     if (lane == 0) p.tail_row[task] = tail;
+    trace_task(p.trace, task, t_task0);
     if (!DYN) break;
     }
 }

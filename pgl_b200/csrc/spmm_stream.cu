@@ -67,6 +67,7 @@ struct StreamP {
     int accumulate;          // SUM only: out = (out_prev + sum) * scale_dst
     int hot_mode;            // 1: hot=evict_last cold=evict_first, 2: hot=last cold=normal, 3: hot=normal cold=first
     unsigned *counter;       // task queue head of the persistent (DYN) kernels, zeroed by task_plan_kernel
+    long long *trace;        // debug, nullable: [ntasks, 4] = (start ns, end ns, SM id, warp slot) per task (pglb_debug_task_trace)
     float *lse;              // YM 2, nullable: [n_rows, H] log-sum-exp of every non-empty row's logits (saved for backward)
     int dyn;                 // 0: static block -> task map, 1: dynamic ascending, 2: dynamic descending
 };
@@ -115,6 +116,27 @@ __device__ __forceinline__ float4 lds128(unsigned addr) {
     return v;
 }
 
+__device__ __forceinline__ long long global_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned sm_id() {
+    unsigned v;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(v));
+    return v;
+}
+// one record per task, written by lane 0 when a debug buffer is armed
+__device__ __forceinline__ void trace_task(long long *trace, int64_t task, long long t0) {
+    if (trace && (threadIdx.x & 31) == 0) {
+        long long *r = trace + task * 4;
+        r[0] = t0;
+        r[1] = global_ns();
+        r[2] = sm_id();
+        r[3] = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    }
+}
+
 // upper_bound(indptr[0..n_rows], v) - 1 : the non-empty row containing slot v
 __device__ __forceinline__ int64_t row_of_slot(const int64_t *__restrict__ indptr, int64_t n_rows,
                                                int64_t v) {
@@ -131,6 +153,31 @@ __device__ __forceinline__ int64_t row_of_slot(const int64_t *__restrict__ indpt
 // search out of their register allocation and instruction stream
 __device__ __noinline__ int64_t row_of_slot_cold(const int64_t *indptr, int64_t n_rows, int64_t v) {
     return row_of_slot(indptr, n_rows, v);
+}
+
+// The same answer when the caller knows a row `from` with indptr[from] <= v: gallop (from + 1, + 2, + 4, ...) to a
+// row whose start lies beyond v, then bisect the last window.  A run of k empty rows costs ~2 log2(k) loads, the first
+// few from the cache line the streaming kernels just read -- instead of the ~log2(n_rows) dependent L2 / DRAM loads
+// of the full search.  (RMAT's sparse tail has an empty run after every other one-edge row: at 20 dependent loads
+// per jump those tasks ran ~10x longer than the rest and kept a few SMs busy long after the others had finished.)
+__device__ __noinline__ int64_t row_of_slot_from(const int64_t *indptr, int64_t n_rows, int64_t from, int64_t v) {
+    int64_t lo = from, hi, step = 1;
+    for (;;) {
+        hi = lo + step;
+        if (hi >= n_rows) {
+            hi = n_rows;   // indptr[n_rows] = E > v
+            break;
+        }
+        if (__ldg((const long long *)indptr + hi) > v) break;
+        lo = hi;
+        step <<= 1;
+    }
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg((const long long *)indptr + mid) > v) hi = mid;
+        else lo = mid;
+    }
+    return lo;
 }
 
 __global__ void __launch_bounds__(256) task_plan_kernel(const int64_t *__restrict__ indptr,
@@ -283,7 +330,7 @@ __global__ void __launch_bounds__(Geo<CFG, YM>::kWarps * 32, 2) spmm_stream128_k
                     row = p.n_rows;
                     end_rel = 1 << 30;
                 } else {
-                    row = row_of_slot_cold(p.indptr, p.n_rows, pos_abs);
+                    row = row_of_slot_from(p.indptr, p.n_rows, row, pos_abs);
                     end_rel = rel(ld_ro(p.indptr + row + 1));
                     nxt_rel = (row + 2 <= p.n_rows) ? rel(ld_ro(p.indptr + row + 2)) : (1 << 30);
                 }
@@ -533,7 +580,7 @@ __global__ void __launch_bounds__(StreamCfg<ITERS>::kThreads) spmm_stream_kernel
                 if (cur_beg >= p.E) {
                     row = p.n_rows;
                 } else {
-                    row = row_of_slot_cold(p.indptr, p.n_rows, cur_beg);
+                    row = row_of_slot_from(p.indptr, p.n_rows, row, cur_beg);
                     cur_end = ld_ro(p.indptr + row + 1);
                 }
             }
@@ -862,7 +909,7 @@ __global__ void __launch_bounds__(Geo<1, 0>::kWarps * 32, 2) spmm_narrow_kernel(
                     row = p.n_rows;
                     end_rel = 1 << 30;
                 } else {
-                    row = row_of_slot_cold(p.indptr, p.n_rows, pos_abs);
+                    row = row_of_slot_from(p.indptr, p.n_rows, row, pos_abs);
                     end_rel = rel(ld_ro(p.indptr + row + 1));
                     nxt_rel = (row + 2 <= p.n_rows) ? rel(ld_ro(p.indptr + row + 2)) : (1 << 30);
                 }
@@ -1095,6 +1142,14 @@ static int dyn_mode(const char *name, int slot, int64_t ntasks) {
     return ntasks >= 8 * resident_warps ? 1 : 2;
 }
 
+// debug: per-task timeline of the next launches of spmm_v5_kernel / spmm_gat5_kernel (scripts/task_trace.py)
+static std::atomic<long long *> g_trace{nullptr};
+static std::atomic<int64_t> g_trace_cap{0};
+static long long *trace_for(int64_t ntasks) {
+    long long *t = g_trace.load(std::memory_order_acquire);
+    return (t && ntasks <= g_trace_cap.load(std::memory_order_acquire)) ? t : nullptr;
+}
+
 static int stream_cfg() {
     static int c = -1;
     if (c < 0) {
@@ -1199,6 +1254,7 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
     }
     p.counter = w.counter;
     p.dyn = dyn_mode("PGLB_V5_DYN", 0, w.ntasks);
+    p.trace = trace_for(w.ntasks);
     {
         const int64_t blocks = (w.ntasks + 1 + 255) / 256;
         task_plan_kernel<<<(unsigned)blocks, 256, 0, stream>>>(indptr, n_dst, E, T, stream_snap(T),
@@ -1393,6 +1449,7 @@ int gat_fused_run(const int64_t *indptr, const int64_t *cols, const float *f, in
     p.hot_mode = 1;
     p.counter = w.counter;
     p.dyn = dyn_mode("PGLB_GAT_DYN", 1, w.ntasks);
+    p.trace = trace_for(w.ntasks);
     p.lse = lse;
     // the row statistics are written by spmm_gat5_kernel and the merge kernel only
     PGLB_CHECK_ARG(!lse || gat5_eligible(p, f, ldf, attn_src, H, n_src), PGLB_EUNSUPPORTED,
@@ -1414,6 +1471,12 @@ int gat_fused_run(const int64_t *indptr, const int64_t *cols, const float *f, in
 }  // namespace pglb
 
 using namespace pglb;
+
+extern "C" int pglb_debug_task_trace(void *buffer, int64_t capacity_tasks) {
+    g_trace_cap.store(buffer ? capacity_tasks : 0, std::memory_order_release);
+    g_trace.store(reinterpret_cast<long long *>(buffer), std::memory_order_release);
+    return PGLB_OK;
+}
 
 extern "C" int pglb_spmm_narrow_ws(int64_t num_edges, int64_t D, size_t *ws_bytes) {
     PGLB_CHECK_ARG(ws_bytes != nullptr && num_edges >= 0 && D > 0, PGLB_EINVAL, "pglb_spmm_narrow_ws: bad argument");

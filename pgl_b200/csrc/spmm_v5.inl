@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_v5_kernel(const StreamP p, con
     } else {
         task = (int64_t)blockIdx.x * W + wib;
     }
+    const long long t_task0 = p.trace ? global_ns() : 0;
     const int64_t a = ld_ro(p.start + task);
     const int64_t b = ld_ro(p.start + task + 1);
     const int cnt = (int)(b - a);
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_v5_kernel(const StreamP p, con
                     row = p.n_rows;
                     end_rel = 1 << 30;
                 } else {
-                    row = row_of_slot_cold(p.indptr, p.n_rows, pos_abs);
+                    row = row_of_slot_from(p.indptr, p.n_rows, row, pos_abs);
                     end_rel = rel(ld_ro(p.indptr + row + 1));
                     nxt_rel = (row + 2 <= p.n_rows) ? rel(ld_ro(p.indptr + row + 2)) : (1 << 30);
                 }
@@ -336,6 +337,7 @@ __global__ void __launch_bounds__(W * 32, 2) spmm_v5_kernel(const StreamP p, con
         if (DYN && ISSUE == 1) gtot += (unsigned)ngroups;
     }
     if (lane == 0) p.tail_row[task] = tail;
+    trace_task(p.trace, task, t_task0);
     if (!DYN) break;
     }
 }
