@@ -1122,22 +1122,34 @@ int64_t stream_task_size(int64_t E) {
 // order, bit-identical to the sequential loop).
 static int64_t stream_snap(int64_t T) { return env_task_size() ? T : (T > 1024 ? T : 1024); }
 
-size_t stream_ws_bytes(int64_t E, int64_t D) { return stream_layout(nullptr, E, D, stream_task_size(E)).bytes; }
+// The fused GAT kernel runs on the device-side queue in descending task order and likes tasks half as long
+// (cfg3: 1.08 ms at T = 608, 0.89 ms at 320, 0.93 ms at 160; profiles/r02_task_trace.log).
+static int64_t gat_task_size(int64_t E) {
+    const int64_t fixed = env_task_size();
+    if (fixed) return fixed;
+    int64_t t = (stream_task_size(E) / 2 + 31) / 32 * 32;
+    return t < 32 ? 32 : t;
+}
+
+// one workspace size for every kernel of the family: the layout of the smallest task size any of them uses
+size_t stream_ws_bytes(int64_t E, int64_t D) { return stream_layout(nullptr, E, D, gat_task_size(E)).bytes; }
 
 // Task hand-out of the persistent kernels (spmm_v5 / spmm_gat5): 0 = static block -> task map, 1 = device-side queue
 // in ascending task order, 2 = queue in descending order.  slot 0: PGLB_V5_DYN, slot 1: PGLB_GAT_DYN (read per
 // call -- a getenv, no cache -- so one process can compare the modes).
-// Defaults (measured, profiles/r02_dyn_sweep.log): the copy-sum kernel gains 4-8 % from the queue -- ascending order
-// when there are many tasks per resident warp (cfg5 on one GPU: 8.64 -> 8.32 ms), descending when there are few (one
-// rank's 12.5M-edge shard of the 8 x 1 grid: 1.34 -> 1.24 ms); the fused GAT kernel does not (2.15 static, 2.18
-// descending, 2.92 ascending on cfg3) and keeps the static map.
+// Defaults (measured, profiles/r02_dyn_sweep*.log, r02_task_trace.log): the copy-sum kernel gains 4-8 % from the
+// queue -- ascending order when there are many tasks per resident warp (cfg5 on one GPU: 8.05 -> 7.74 ms), descending
+// when there are few (one rank's 12.5M-edge shard of the 8 x 1 grid: 1.29 -> 1.19 ms).  The fused GAT kernel on RMAT
+// gains most from the DESCENDING queue (1.79 static, 1.54 ascending, 1.08 descending; 0.89 with half-size tasks): RMAT
+// puts the expensive tasks (one-edge rows) last, the descending queue starts them first and every warp stays busy to the
+// end (static map: busy warps fall from 1600 to 0 over the last 40 % of the launch).
 static int dyn_mode(const char *name, int slot, int64_t ntasks) {
     const char *e = getenv(name);
     if (e) {
         const int v = atoi(e);
         if (v >= 0 && v <= 2) return v;
     }
-    if (slot == 1) return 0;
+    if (slot == 1) return 2;
     const int64_t resident_warps = (int64_t)sm_count() * 2 * 13;
     return ntasks >= 8 * resident_warps ? 1 : 2;
 }
@@ -1416,7 +1428,7 @@ int gat_fused_run(const int64_t *indptr, const int64_t *cols, const float *f, in
                   int64_t ldo, int64_t n_dst, int64_t n_src, int64_t E, int64_t D, int64_t H,
                   const float *attn_src, const float *attn_dst, float slope, float *lse, void *ws, size_t ws_bytes,
                   cudaStream_t stream) {
-    const int64_t T = stream_task_size(E);
+    const int64_t T = gat_task_size(E);
     PGLB_CHECK_ARG(E > 0, PGLB_EINVAL, "gat_fused_run: needs at least one slot");
     StreamWs w = stream_layout(ws, E, D, T);
     PGLB_CHECK_ARG(ws != nullptr && ws_bytes >= w.bytes, PGLB_EWORKSPACE,
