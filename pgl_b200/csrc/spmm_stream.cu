@@ -247,8 +247,6 @@ __global__ void __launch_bounds__(Geo<CFG, YM>::kWarps * 32, 2) spmm_stream128_k
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
-    const int64_t task = (int64_t)blockIdx.x * W + wib;
-    if (task >= p.ntasks) return;
     const unsigned smem0 = (unsigned)__cvta_generic_to_shared(smem_raw);
     const unsigned ring = smem0 + wib * (RING * 512) + lane * 16;
     const unsigned ring2 = smem0 + W * (RING * 512) + wib * (RING * 128) + lane * 4;
@@ -267,6 +265,24 @@ __global__ void __launch_bounds__(Geo<CFG, YM>::kWarps * 32, 2) spmm_stream128_k
     const char *xlane = reinterpret_cast<const char *>(p.x) + (act ? lane * 16 : 0);
     const unsigned row_bytes = (unsigned)(p.ldx * 4);
 
+    // p.dyn != 0: persistent warps draw task ids from the device-side queue (see spmm_v5_kernel); the per-lane
+    // cp.async rings are drained at the end of every task, so a task starts from a clean ring either way
+#pragma unroll 1
+    for (;;) {
+    int64_t task;
+    if (p.dyn) {
+        unsigned t = 0;
+        if (lane == 0) t = atomicAdd(p.counter, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if ((int64_t)t >= p.ntasks) break;
+        task = p.dyn == 2 ? p.ntasks - 1 - (int64_t)t : (int64_t)t;
+    } else {
+        task = (int64_t)blockIdx.x * W + wib;
+        if (task >= p.ntasks) break;
+    }
+    m_run = -INFINITY;
+    l_run = 0.0f;
+    ad = 0.0f;
     const int64_t a = ld_ro(p.start + task);
     const int64_t b = ld_ro(p.start + task + 1);
     const int cnt = (int)(b - a);
@@ -493,6 +509,9 @@ __global__ void __launch_bounds__(Geo<CFG, YM>::kWarps * 32, 2) spmm_stream128_k
         }
     }
     if (lane == 0) p.tail_row[task] = tail;
+    if (!p.dyn) break;
+    cp_async_wait<0>();   // nothing real is pending; keeps the group count of the next task's pipeline exact
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1149,7 +1168,7 @@ static int dyn_mode(const char *name, int slot, int64_t ntasks) {
         const int v = atoi(e);
         if (v >= 0 && v <= 2) return v;
     }
-    if (slot == 1) return 2;
+    if (slot >= 1) return 2;
     const int64_t resident_warps = (int64_t)sm_count() * 2 * 13;
     return ntasks >= 8 * resident_warps ? 1 : 2;
 }
@@ -1178,8 +1197,9 @@ static int launch_stream128_cfg(const StreamP &p, cudaStream_t stream) {
     const int smem = G_::kSmem;
     static std::atomic<unsigned long long> attr_done{0};
     PGLB_CUDA(ensure_dyn_smem(spmm_stream128_kernel<RK, SCALED, PK, YM, CFG>, smem, attr_done));
-    const int64_t blocks = (p.ntasks + W - 1) / W;
+    int64_t blocks = (p.ntasks + W - 1) / W;
     PGLB_CHECK_ARG(blocks <= 0x7fffffffLL, PGLB_ESHAPE, "spmm_stream: grid too large");
+    if (p.dyn && blocks > (int64_t)sm_count() * 2) blocks = (int64_t)sm_count() * 2;   // persistent: 2 CTAs per SM
     spmm_stream128_kernel<RK, SCALED, PK, YM, CFG><<<(unsigned)blocks, W * 32, smem, stream>>>(p);
     PGLB_LAUNCH_CHECK("spmm_stream128_kernel");
     const int64_t fblocks = (p.ntasks * 32 + 255) / 256;
@@ -1289,6 +1309,7 @@ int spmm_stream_run(const int64_t *indptr, const int64_t *cols, const float *x, 
     }
     if (cv <= 32 && v5_eligible(p, n_src, rk, small_ids))
         return launch_v5(p, n_src, cols32 != nullptr && cols != nullptr && l2_hints != 0, stream);
+    p.dyn = dyn_mode("PGLB_S128_DYN", 2, w.ntasks);   // round 1's kernel (max / min, edge operands): descending queue
     if (cv <= 32 && small_ids) {
         if (y) {  // edge operand: plain int64 ids, no source scale
             return rk ? launch_stream128<1, false, 0, 1>(p, stream) : launch_stream128<0, false, 0, 1>(p, stream);
