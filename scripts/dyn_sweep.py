@@ -68,6 +68,54 @@ def gcn_case(dev, n, e, d, rr, r, label):
     torch.cuda.empty_cache()
 
 
+def sage_case(dev):
+    """cfg4's aggregation: mean over the products-shape stand-in, D = 100 and 128 (+ a task timeline per mode)."""
+    from pgl_b200._lib import check, lib
+    n, und = 2_449_029, 61_859_140
+    half = bench.gen_edges(torch, n, und, 0.6, 5, dev)
+    edges = torch.cat([half, half.flip(1)], 0)
+    del half
+    e = int(edges.shape[0])
+    g = pgl.Graph(edges=edges, num_nodes=n)
+    g._fwd_csr()
+    cap = 1 << 17
+    buf = torch.zeros(cap, 4, dtype=torch.int64, device=dev)
+    for d in (100, 128):
+        x = bench.gen_features(torch, n, d, 4, dev)
+        base = None
+        with torch.no_grad():
+            for mode in (0, 1, 2, 0):
+                os.environ["PGLB_V5_DYN"] = str(mode)
+                mean, best = time_steps(lambda: g.send_recv(x, "mean"), steps=8, warm=3)
+                got = g.send_recv(x, "mean").clone()
+                if base is None:
+                    base = got
+                buf.zero_()
+                check(lib.pglb_debug_task_trace(ops._ptr(buf), cap))
+                g.send_recv(x, "mean")
+                torch.cuda.synchronize()
+                check(lib.pglb_debug_task_trace(None, 0))
+                tr = buf.cpu().numpy()
+                tr = tr[tr[:, 1] > 0]
+                t0 = tr[:, 0].min()
+                st, en = (tr[:, 0] - t0) / 1e3, (tr[:, 1] - t0) / 1e3
+                dur = en - st
+                nt = len(tr)
+                nb = 10
+                te = np.linspace(0, en.max(), nb + 1)
+                busy = [round(float(np.clip(np.minimum(en, te[i + 1]) - np.maximum(st, te[i]), 0, None).sum() / (te[i + 1] - te[i])), 0)
+                        for i in range(nb)]
+                dec = [round(float(dur[i * nt // 10:(i + 1) * nt // 10].mean()), 0) for i in range(10)]
+                b_alg = e * (4 * d + 8) + n * 4 * d + (n + 1) * 8
+                print(json.dumps({"case": "cfg4 mean aggregation D=%d" % d, "dyn": mode, "ms_mean": mean, "ms_min": best,
+                                  "frac_of_6582": b_alg / (mean * 1e-3) / 1e9 / 6582.5,
+                                  "bit_identical": bool(torch.equal(got, base)), "tasks": nt, "span_us": round(float(en.max()), 0),
+                                  "dur_p50_p99_max": [round(float(np.percentile(dur, q)), 0) for q in (50, 99, 100)],
+                                  "mean_dur_by_task_decile": dec, "busy_warps": busy}), flush=True)
+        del x
+    os.environ.pop("PGLB_V5_DYN", None)
+
+
 def gat_case(dev):
     n, e, H, Dh = 1 << 20, 10_000_000, 8, 16
     edges = bench.rmat_edges(torch, 20, e, seed=1, device=dev)
@@ -98,6 +146,8 @@ if __name__ == "__main__":
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     what = sys.argv[1:] or ["gat", "shard", "full"]
+    if "sage" in what:
+        sage_case(dev)
     if "gat" in what:
         gat_case(dev)
     if "shard" in what:
