@@ -405,11 +405,11 @@ def read_traffic(key):
     return None
 
 
-def kernel_name():
+def kernel_name(num_edges=None, num_rows=None):
     v5 = os.environ.get("PGLB_STREAM_V5")
     try:
         from pgl_b200 import ops
-        return ops.stream_kernel_name()
+        return ops.stream_kernel_name(num_edges, num_rows)
     except Exception:
         return "spmm_stream (PGLB_STREAM_V5=%s)" % v5
 
@@ -632,7 +632,7 @@ def bench_gcn(args, torch, dist, pgl, ops, GF, dev, world, rank):
                      "note": "the least efficient rank's kernel: E_r*(4*Dl+8) + N_r*4*Dl + (N_r+1)*8 + 2*N_r*4 bytes "
                              "(its edges, its rows, Dl = %d columns) over its mean kernel time (CUDA events around each "
                              "step on the launching stream)" % dl,
-                     "kernel": kernel_name() if dl > 64 else "spmm_narrow2_kernel (+ empty_rows, fix-up kernels)",
+                     "kernel": kernel_name(e_loc, n_loc) if dl > 64 else "spmm_narrow2_kernel (+ empty_rows, fix-up kernels)",
                      "kernel_ms_mean": kern_ms,
                      "kernel_ms_p10": per[len(per) // 10], "kernel_ms_p90": per[(len(per) * 9) // 10]},
         "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -1209,7 +1209,7 @@ def bench_sage(args, torch, dist, pgl, ops, GF, dev, world, rank):
                                   "32-byte sectors for 12.5 useful (sector efficiency 0.89-0.96)"},
         "roofline": {"bound": "hbm", "achieved": agg0["agg_alg_GBs"], "peak": hbm_gbs, "unit": "GB/s",
                      "frac": agg0["agg_roofline_frac"], "traffic": read_traffic("sage_l1_bytes_per_launch"),
-                     "peak_source": peak_src, "kernel": kernel_name(),
+                     "peak_source": peak_src, "kernel": kernel_name(e, n),
                      "note": "layer-1 mean aggregation (D = 100): E*(4D+8) + N*4D + (N+1)*8 = 416 B/edge model"},
         "parity": parity, "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
     }

@@ -386,15 +386,25 @@ static int v5_mode() {
     }
     return v;
 }
-// PGLB_V5_GEO: 0 = groups of 4, ring of 4, 13 warps per CTA; 1 = groups of 8, ring of 4, 6 warps; 2 = groups of 8, ring of 3, 9 warps
-static int v5_geo() {
-    static int v = -1;
-    if (v < 0) {
+// Ring geometry.  0 = groups of 4, ring of 4, 13 warps per CTA; 1 = groups of 8, ring of 4, 6 warps; 2 = groups of 8,
+// ring of 3, 9 warps.  PGLB_V5_GEO pins one; otherwise the average row length decides (measured at the two ends,
+// profiles/r02_v5_geo_sweep_cfg4.log): sparse graphs (cfg5, 10 slots per row) want many warps and small groups -- the
+// gathers go to DRAM and most groups straddle a row boundary (geometry 1 there: 10.8 ms against 8.45); dense graphs
+// (cfg4's products-shape stand-in, 50 slots per row, gathers mostly L2 hits) are bound by instruction issue, and the
+// fully unrolled 8-row group halves it: 14.0 -> 7.7 ms per aggregation.
+static int v5_geo_env() {
+    static int v = -2;
+    if (v == -2) {
         const char *e = getenv("PGLB_V5_GEO");
-        v = e ? atoi(e) : 0;
-        if (v < 0 || v > 2) v = 0;
+        v = e ? atoi(e) : -1;
+        if (v < -1 || v > 2) v = -1;
     }
     return v;
+}
+static int v5_geo(const StreamP &p) {
+    const int e = v5_geo_env();
+    if (e >= 0) return e;
+    return (p.n_rows > 0 && p.E >= 24 * p.n_rows) ? 2 : 0;
 }
 
 template <int ISSUE, bool SCALED, bool D128, bool HOT, int GRP, int NG, int W>
@@ -427,7 +437,7 @@ static int launch_v5_geo(const StreamP &p, const CUtensorMap &tm, cudaStream_t s
 
 template <int ISSUE, bool SCALED, bool D128, bool HOT>
 static int launch_v5_h(const StreamP &p, const CUtensorMap &tm, cudaStream_t stream) {
-    switch (v5_geo()) {
+    switch (v5_geo(p)) {
         case 1: return launch_v5_geo<ISSUE, SCALED, D128, HOT, 8, 4, 6>(p, tm, stream);
         case 2: return launch_v5_geo<ISSUE, SCALED, D128, HOT, 8, 3, 9>(p, tm, stream);
         default: return launch_v5_geo<ISSUE, SCALED, D128, HOT, 4, 4, 13>(p, tm, stream);
