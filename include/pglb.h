@@ -238,6 +238,13 @@ int pglb_gat_fused_csr_f32(const int64_t *indptr, const int64_t *cols, const flo
                            float *out, int64_t ldo, int64_t n_dst, int64_t n_src, int64_t num_edges,
                            int64_t H, int64_t head_dim, void *ws, size_t ws_bytes, void *stream);
 
+/* GATConv's attention projections (pgl/nn/conv.py:323-326: paddle.sum(feature * weight_src, -1) and the same with
+ * weight_dst -- two multiplies, two reductions, two [N, H, head_dim] temporaries) in one pass over f:
+ *   attn_src[n,h] = <f[n,h,:], w_src[h,:]>,  attn_dst[n,h] = <f[n,h,:], w_dst[h,:]>.
+ * f rows of H*head_dim <= 128 floats, 16-byte aligned; head_dim in {4, 8, ..., 128}. */
+int pglb_head_dots_f32(const float *f, int64_t ldf, int64_t n, int64_t H, int64_t head_dim, const float *w_src,
+                       const float *w_dst, float *attn_src, float *attn_dst, void *stream);
+
 /* Training forward of the same layer (GATConv under autograd, pgl/nn/conv.py:333-339; the reference gets the
  * backward from Paddle autograd over four ops): the same single launch, which also leaves
  *   lse[d,h] = log sum_j exp(leaky_relu(attn_src[cols[j],h] + attn_dst[d,h]))

@@ -73,6 +73,7 @@ _SIGS = {
     "pglb_linear_tf32x3_f32": (c_int, [_p, _i64, _p, _p, _p, _i64, _i64, _i64, _i64, c_int, _p]),
     "pglb_gat_fused_csr_f32": (c_int, [_p, _p, _p, _i64, _p, _p, ctypes.c_float, _p, _i64, _i64, _i64, _i64,
                                        _i64, _i64, _p, c_size_t, _p]),
+    "pglb_head_dots_f32": (c_int, [_p, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p]),
     "pglb_gat_fused_train_csr_f32": (c_int, [_p, _p, _p, _i64, _p, _p, ctypes.c_float, _p, _i64, _p, _i64, _i64,
                                              _i64, _i64, _i64, _p, c_size_t, _p]),
     "pglb_gat_bwd_edge_f32": (c_int, [_p, _p, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, ctypes.c_float,

@@ -283,6 +283,58 @@ __global__ void __launch_bounds__(256) degree_norm_kernel(const int64_t *__restr
     }
 }
 
+
+// GATConv's two attention projections in one pass over the transformed features (reference pgl/nn/conv.py:323-326:
+// attn_src = sum(feature * weight_src, -1), attn_dst = sum(feature * weight_dst, -1) -- four elementwise / reduce
+// launches and two [N, H, Dh] temporaries there):  as[n,h] = <f[n,h,:], ws[h,:]>,  ad[n,h] = <f[n,h,:], wd[h,:]>.
+// A warp per row, a float4 per lane, LPH = Dh / 4 lanes per head (shuffle reduce), weights in registers.
+template <int LPH>
+__global__ void __launch_bounds__(256) head_dots_kernel(const float *__restrict__ f, int64_t ldf, int64_t n, int D,
+                                                        int H, const float *__restrict__ ws,
+                                                        const float *__restrict__ wd, float *__restrict__ as,
+                                                        float *__restrict__ ad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const bool act = lane * 4 < D;
+    const int head = act ? lane / LPH : 0;
+    const bool lead = act && (lane % LPH) == 0;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (act) {
+        a = __ldg(reinterpret_cast<const float4 *>(ws + lane * 4));
+        b = __ldg(reinterpret_cast<const float4 *>(wd + lane * 4));
+    }
+    auto head_sum = [&](float v) {
+#pragma unroll
+        for (int o = LPH / 2; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    };
+    constexpr int U = 4;
+    for (int64_t r0 = warp * U; r0 < n; r0 += nwarps * U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (act && r0 + u < n) v[u] = __ldg(reinterpret_cast<const float4 *>(f + (r0 + u) * ldf + lane * 4));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            // products rounded one by one and added in index order inside the lane, like the elementwise multiply +
+            // sum they replace; the LPH partial sums are combined by the shuffle tree
+            float s = __fmul_rn(v[u].x, a.x), d = __fmul_rn(v[u].x, b.x);
+            s = __fadd_rn(s, __fmul_rn(v[u].y, a.y)); d = __fadd_rn(d, __fmul_rn(v[u].y, b.y));
+            s = __fadd_rn(s, __fmul_rn(v[u].z, a.z)); d = __fadd_rn(d, __fmul_rn(v[u].z, b.z));
+            s = __fadd_rn(s, __fmul_rn(v[u].w, a.w)); d = __fadd_rn(d, __fmul_rn(v[u].w, b.w));
+            s = head_sum(s);
+            d = head_sum(d);
+            if (lead && r0 + u < n) {
+                as[(r0 + u) * H + head] = s;
+                ad[(r0 + u) * H + head] = d;
+            }
+        }
+    }
+}
+
 static inline bool a16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int lane_shift(int64_t dv) {  // lanes per row = min(32, next pow2 >= dv)
     int l = 0;
@@ -456,6 +508,33 @@ extern "C" int pglb_degree_norm_f32(const int64_t *degree, int64_t n, float *nor
     PGLB_CHECK_ARG(degree && norm, PGLB_EINVAL, "pglb_degree_norm_f32: NULL pointer");
     degree_norm_kernel<<<grid_for(n), 256, 0, stream>>>(degree, n, norm);
     PGLB_LAUNCH_CHECK("degree_norm_kernel");
+    return PGLB_OK;
+}
+
+extern "C" int pglb_head_dots_f32(const float *f, int64_t ldf, int64_t n, int64_t H, int64_t head_dim,
+                                  const float *w_src, const float *w_dst, float *attn_src, float *attn_dst,
+                                  void *stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    PGLB_CHECK_ARG(n >= 0 && H > 0 && head_dim > 0, PGLB_EINVAL, "pglb_head_dots_f32: bad size");
+    const int64_t D = H * head_dim, lph = head_dim / 4;
+    PGLB_CHECK_ARG(D <= 128 && head_dim % 4 == 0 && (lph & (lph - 1)) == 0, PGLB_EUNSUPPORTED,
+                   "pglb_head_dots_f32: needs H*head_dim <= 128 and head_dim in {4, 8, 16, 32, 64, 128}");
+    if (n == 0) return PGLB_OK;
+    PGLB_CHECK_ARG(f && w_src && w_dst && attn_src && attn_dst, PGLB_EINVAL, "pglb_head_dots_f32: NULL pointer");
+    PGLB_CHECK_ARG(ldf >= D && ldf % 4 == 0 && a16(f) && a16(w_src) && a16(w_dst), PGLB_ESHAPE,
+                   "pglb_head_dots_f32: rows / weights must be 16-byte aligned");
+    const int grid = grid_for(n * 8);   // a warp per 4 rows
+#define PGLB_HD(L) head_dots_kernel<L><<<grid, 256, 0, stream>>>(f, ldf, n, (int)D, (int)H, w_src, w_dst, attn_src, attn_dst)
+    switch ((int)lph) {
+        case 1: PGLB_HD(1); break;
+        case 2: PGLB_HD(2); break;
+        case 4: PGLB_HD(4); break;
+        case 8: PGLB_HD(8); break;
+        case 16: PGLB_HD(16); break;
+        default: PGLB_HD(32); break;
+    }
+#undef PGLB_HD
+    PGLB_LAUNCH_CHECK("head_dots_kernel");
     return PGLB_OK;
 }
 

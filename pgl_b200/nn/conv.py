@@ -182,8 +182,13 @@ class GATConv(nn.Module):
             feature = self.feat_dropout(feature)
         feature = self.linear(feature)
         feature = feature.reshape(-1, self.num_heads, self.hidden_size)
-        attn_src = torch.sum(feature * self.weight_src, dim=-1)
-        attn_dst = torch.sum(feature * self.weight_dst, dim=-1)
+        from .. import ops as _ops
+        dots = _ops.head_dots(feature, self.weight_src, self.weight_dst) if feature.is_cuda else None
+        if dots is not None:      # both projections in one pass over the features
+            attn_src, attn_dst = dots
+        else:
+            attn_src = torch.sum(feature * self.weight_src, dim=-1)
+            attn_dst = torch.sum(feature * self.weight_dst, dim=-1)
         no_attn_drop = self.attn_drop <= 1e-15 or not self.training
         if not torch.is_grad_enabled() and no_attn_drop and type(graph).__name__ == "Graph":
             # inference: send_uv + LeakyReLU + edge_softmax in one kernel (logits never stored),

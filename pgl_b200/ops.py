@@ -1092,6 +1092,53 @@ def gat_fused(csr, f, attn_src, attn_dst, negative_slope=0.2):
     return out.reshape(n_dst, H, Dh)
 
 
+class _HeadDots(torch.autograd.Function):
+    """attn_src / attn_dst of GATConv in one pass over the features (pglb_head_dots_f32); the backward is three
+    elementwise / reduce torch ops on the gradient path."""
+
+    @staticmethod
+    def forward(ctx, f3, w_src, w_dst):
+        n, H, Dh = (int(v) for v in f3.shape)
+        f2 = f3.reshape(n, H * Dh)
+        a_s = torch.empty((n, H), dtype=torch.float32, device=f3.device)
+        a_d = torch.empty((n, H), dtype=torch.float32, device=f3.device)
+        ws, wd = w_src.contiguous(), w_dst.contiguous()
+        with torch.cuda.device(f3.device):
+            check(lib.pglb_head_dots_f32(_ptr(f2), f2.stride(0), n, H, Dh, _ptr(ws), _ptr(wd), _ptr(a_s), _ptr(a_d),
+                                         _stream()))
+        ctx.save_for_backward(f3, w_src, w_dst)
+        return a_s, a_d
+
+    @staticmethod
+    def backward(ctx, g_s, g_d):
+        f3, w_src, w_dst = ctx.saved_tensors
+        gf = gw_s = gw_d = None
+        if ctx.needs_input_grad[0]:
+            gf = g_s.unsqueeze(-1) * w_src + g_d.unsqueeze(-1) * w_dst
+        if ctx.needs_input_grad[1]:
+            gw_s = (g_s.unsqueeze(-1) * f3).sum(0).reshape(w_src.shape)
+        if ctx.needs_input_grad[2]:
+            gw_d = (g_d.unsqueeze(-1) * f3).sum(0).reshape(w_dst.shape)
+        return gf, gw_s, gw_d
+
+
+def head_dots(f, w_src, w_dst):
+    """(sum(f * w_src, -1), sum(f * w_dst, -1)) for f [N, H, Dh], w [H, Dh] (or [1, H, Dh]) -- GATConv's attention
+    projections, reference pgl/nn/conv.py:323-326 -- or None when the shape is outside the kernel (the caller keeps
+    the two torch expressions)."""
+    if f.dim() != 3 or not f.is_cuda or f.dtype != torch.float32 or w_src.dtype != torch.float32:
+        return None
+    n, H, Dh = (int(v) for v in f.shape)
+    lph = Dh // 4
+    if H * Dh > 128 or Dh % 4 or (lph & (lph - 1)) or w_src.numel() != H * Dh or w_dst.numel() != H * Dh:
+        return None
+    if not f.is_contiguous():
+        f = f.contiguous()
+    if f.data_ptr() % 16 or w_src.data_ptr() % 16 or w_dst.data_ptr() % 16:
+        return None
+    return _HeadDots.apply(f, w_src, w_dst)
+
+
 class _GatFused(torch.autograd.Function):
     """The single-pass GAT aggregation under autograd (reference pgl/nn/conv.py:333-339 differentiated by Paddle over
     four ops).  Forward = pglb_gat_fused_train_csr_f32 (one launch; keeps only lse[N, H]).  Backward = one edge kernel

@@ -243,3 +243,32 @@ def test_dynamic_task_queue_large_graph(pgl):
         for mode in (1, 2):
             with env(PGLB_GAT_DYN=mode):
                 assert torch.equal(pgl.ops.gat_fused(g._fwd_csr(), x.reshape(n, 8, 16), a, a, 0.2), gb)
+
+
+# ---------------------------------------------------------------- attention projections
+@pytest.mark.parametrize("H,Dh", [(8, 16), (4, 8), (1, 128), (32, 4), (12, 8), (2, 64)])
+def test_head_dots_match_the_two_torch_expressions(pgl, H, Dh):
+    """pglb_head_dots_f32 == (sum(f * w_src, -1), sum(f * w_dst, -1)) of pgl/nn/conv.py:323-326, forward and backward."""
+    n = 5003
+    gen = torch.Generator(device="cuda").manual_seed(360 + H)
+    f1 = torch.randn(n, H, Dh, device="cuda", generator=gen).requires_grad_(True)
+    ws1 = torch.randn(H, Dh, device="cuda", generator=gen).requires_grad_(True)
+    wd1 = torch.randn(H, Dh, device="cuda", generator=gen).requires_grad_(True)
+    gs = torch.randn(n, H, device="cuda", generator=gen)
+    gd = torch.randn(n, H, device="cuda", generator=gen)
+    got = pgl.ops.head_dots(f1, ws1, wd1)
+    assert got is not None
+    (got[0] * gs + got[1] * gd).sum().backward()
+    f2, ws2, wd2 = [t.detach().clone().requires_grad_(True) for t in (f1, ws1, wd1)]
+    want = (torch.sum(f2 * ws2, dim=-1), torch.sum(f2 * wd2, dim=-1))
+    (want[0] * gs + want[1] * gd).sum().backward()
+    for a, b in zip(got, want):
+        assert rel_err(a.detach().cpu().numpy(), b.detach().cpu().numpy()) <= 1e-6
+    for a, b in ((f1, f2), (ws1, ws2), (wd1, wd2)):
+        assert rel_err(a.grad.cpu().numpy(), b.grad.cpu().numpy()) <= 1e-5
+    # shapes outside the kernel: the caller keeps the torch expressions
+    assert pgl.ops.head_dots(torch.randn(10, 8, 12, device="cuda"), torch.randn(8, 12, device="cuda"),
+                             torch.randn(8, 12, device="cuda")) is None          # head_dim not a power of two
+    assert pgl.ops.head_dots(torch.randn(10, 16, 16, device="cuda"), torch.randn(16, 16, device="cuda"),
+                             torch.randn(16, 16, device="cuda")) is None         # 256 floats per row
+    assert pgl.ops.head_dots(f1.double(), ws1, wd1) is None
