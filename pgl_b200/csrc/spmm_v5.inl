@@ -387,11 +387,14 @@ static int v5_mode() {
     return v;
 }
 // Ring geometry.  0 = groups of 4, ring of 4, 13 warps per CTA; 1 = groups of 8, ring of 4, 6 warps; 2 = groups of 8,
-// ring of 3, 9 warps.  PGLB_V5_GEO pins one; otherwise the average row length decides (measured at the two ends,
-// profiles/r02_v5_geo_sweep_cfg4.log): sparse graphs (cfg5, 10 slots per row) want many warps and small groups -- the
-// gathers go to DRAM and most groups straddle a row boundary (geometry 1 there: 10.8 ms against 8.45); dense graphs
-// (cfg4's products-shape stand-in, 50 slots per row, gathers mostly L2 hits) are bound by instruction issue, and the
-// fully unrolled 8-row group halves it: 14.0 -> 7.7 ms per aggregation.
+// ring of 3, 9 warps.  PGLB_V5_GEO pins one; otherwise the average row length decides.  Measured (128-float rows, sum;
+// profiles/r02_v5_geo_sweep*.log), geometry 0 vs 2:
+//     slots per row      6       10      10 (cfg5)   16      24      16 (10M nodes)   24 (10M)   50 (cfg4, mean)
+//     geometry 0, ms    0.96    1.35     8.45       3.23    5.31       16.0            25.5        14.0
+//     geometry 2, ms    1.00    1.28     8.98       1.81    2.44        9.8            14.2         7.7
+// Up to ~10 slots per row most groups straddle a row boundary and the many-warps geometry holds its own (cfg5: 6 %
+// better); from 16 slots per row on the fully unrolled 8-row group is 1.6-2.2x faster, whatever the size of the feature
+// matrix.  The switch sits at 12.
 static int v5_geo_env() {
     static int v = -2;
     if (v == -2) {
@@ -404,7 +407,7 @@ static int v5_geo_env() {
 static int v5_geo(const StreamP &p) {
     const int e = v5_geo_env();
     if (e >= 0) return e;
-    return (p.n_rows > 0 && p.E >= 24 * p.n_rows) ? 2 : 0;
+    return (p.n_rows > 0 && p.E >= 12 * p.n_rows) ? 2 : 0;
 }
 
 template <int ISSUE, bool SCALED, bool D128, bool HOT, int GRP, int NG, int W>

@@ -1312,12 +1312,12 @@ def launch_count():
 
 def stream_kernel_name(num_edges=None, num_rows=None):
     """Which wide-row streaming kernel pglb_spmm_csr_f32 routes copy-sum aggregations to (PGLB_STREAM_V5, PGLB_V5_GEO,
-    PGLB_V5_DYN; mirrors csrc/spmm_v5.inl v5_mode() / v5_geo(): without PGLB_V5_GEO, graphs of >= 24 slots per row
+    PGLB_V5_DYN; mirrors csrc/spmm_v5.inl v5_mode() / v5_geo(): without PGLB_V5_GEO, graphs of >= 12 slots per row
     take the groups-of-8 geometry)."""
     v = os.environ.get("PGLB_STREAM_V5", "1")
     g = os.environ.get("PGLB_V5_GEO")
     if g not in ("0", "1", "2"):
-        g = "2" if (num_edges is not None and num_rows and num_edges >= 24 * num_rows) else "0"
+        g = "2" if (num_edges is not None and num_rows and num_edges >= 12 * num_rows) else "0"
     geo = {"0": "GRP=4,NG=4,W=13", "1": "GRP=8,NG=4,W=6", "2": "GRP=8,NG=3,W=9"}[g]
     if v == "0":
         return "spmm_stream128_kernel<RK=0,SCALED=1,PK=2,YM=0,CFG=1> (+ task_plan, empty_rows, fix-up kernels)"

@@ -15,9 +15,9 @@ from pgl_b200 import ops  # noqa: E402
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
-n = 2_000_000
+n = int(os.environ.get("GEO_SWEEP_NODES", "2000000"))
 x = bench.gen_features(torch, n, 128, 9, dev)
-for deg in (16, 24, 32, 40):
+for deg in [int(v) for v in os.environ.get("GEO_SWEEP_DEGS", "16,24,32,40").split(",")]:
     edges = bench.gen_edges(torch, n, n * deg, 0.8, 31 + deg, dev)
     g = pgl.Graph(edges=edges, num_nodes=n)
     fwd = g._fwd_csr()
@@ -38,7 +38,7 @@ for deg in (16, 24, 32, 40):
         b.record()
         torch.cuda.synchronize()
         per.append(a.elapsed_time(b))
-    print(json.dumps({"slots_per_row": deg, "geo_env": os.environ.get("PGLB_V5_GEO", "auto"), "ms_mean": float(np.mean(per)),
+    print(json.dumps({"nodes": n, "slots_per_row": deg, "geo_env": os.environ.get("PGLB_V5_GEO", "auto"), "ms_mean": float(np.mean(per)),
                       "ms_min": float(np.min(per)), "G_edges_s": n * deg / np.mean(per) / 1e6}), flush=True)
     del g, fwd, packed, edges
     torch.cuda.empty_cache()
