@@ -311,7 +311,8 @@ int pglb_reindex_graph(const int64_t *x, int64_t n, const int64_t *neighbors, co
 /* Same contract as pglb_memcpy2d_async, but the copy is done by a kernel through the unified address
  * space (zero-copy loads / stores across PCIe; the host side must be pinned memory).  For narrow column
  * blocks, where the copy engine's 2-D transfers run at about half the PCIe rate.  width, pitches and both
- * pointers multiples of 16 bytes; ctas <= 0 -> 16.  EXPERIMENTAL: not yet run on hardware (round 1). */
+ * pointers multiples of 16 bytes; ctas <= 0 -> 16.  Opt-in (PGLB_HOST_COPY=kernel) and unmeasured: the cross-call
+ * pipeline of Graph.host_aggregator removed the need for narrow 2-D copies. */
 int pglb_copy2d_kernel_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes,
                              int64_t height, int ctas, void *stream);
 

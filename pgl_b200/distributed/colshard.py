@@ -7,10 +7,11 @@ aggregation is independent per column, so it needs no exchange at all; one all-t
 result back.  Exchange volume per GPU is N*D*4/R bytes per direction whatever the graph looks like
 (0.64 GB at cfg5 / 8 GPUs), against 2.1-2.5 GB of halo rows per rank for the row partition of a power-law
 graph.  The price is narrow rows (D/R floats): they need the narrow-row streaming
-kernel (csrc/spmm_stream.cu, PGLB_NARROW=1).
+kernel (csrc/spmm_narrow2.inl, the default for rows of <= 64 floats).
 
-EXPERIMENTAL: written after round 1's GPU budget was spent.  The re-shard logic is covered by a world-2
-gloo test on CPU; the aggregation path has not run on hardware.
+Status: the re-shard logic is covered by a world-2 gloo test on CPU and runs under NCCL in bench.py's full_layer
+leg on every grid; the narrow-row aggregation was validated and measured on hardware in round 2 (DESIGN.md
+sections 4.2b and 5.1 -- it is why the bench default shards destination rows, not columns).
 """
 import torch
 import torch.distributed as dist

@@ -559,8 +559,7 @@ class _MaxMinAgg(torch.autograd.Function):
         return gx, None, None, None, None
 
 
-# PGLB_NARROW=1 (experimental): rows of <= 64 floats take the narrow-row streaming kernel, which reads
-# packed column ids like the wide-row kernel
+# rows of <= 64 floats: spmm_narrow2_kernel by default; PGLB_NARROW=1 PGLB_NARROW2=0 selects round 1's narrow kernel
 NARROW2 = os.environ.get("PGLB_NARROW2", "1") != "0"          # spmm_narrow2_kernel for copy-sum / mean over rows of <= 64 floats
 NARROW_ROWS = os.environ.get("PGLB_NARROW") == "1"            # round 1's spmm_narrow_kernel (opt-in, superseded)
 

@@ -1,7 +1,7 @@
 """NeighborSampler: layer-wise uniform neighbour sampling on the device for mini-batch GraphSAGE
 (reference pgl/sampling/sage.py:130-155).  ``sample_neighbors`` / ``reindex_graph`` stand in for
 ``paddle.geometric.sample_neighbors`` / ``paddle.geometric.reindex_graph`` on the sm_100a kernels of
-csrc/sampling.cu.  EXPERIMENTAL (not yet validated on hardware)."""
+csrc/sampling.cu (validated on hardware in round 2: tests/test_gpu_sampling.py)."""
 import ctypes
 
 import torch
