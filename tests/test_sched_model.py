@@ -130,3 +130,66 @@ def test_geometry_and_queue_defaults():
     assert geo(100_000_000, 10_000_000) == 0 and geo(12_500_044, 1_184_431) == 0      # cfg5 and its 8 x 1 shard
     assert geo(123_718_280, 2_449_029) == 2                                            # cfg4
     assert dyn(48829) == 1 and dyn(16276) == 2
+
+
+# ---------------------------------------------------------------- csrc/localgraph.cu: the halo plan as flags + prefix sums
+def halo_plan_model(edges, n, lo, hi, offsets):
+    """halo_mark_kernel -> two inclusive scans -> halo_fill_edges_kernel / halo_fill_nodes_kernel /
+    halo_recv_counts_kernel, statement by statement in numpy."""
+    src, dst = edges[:, 0], edges[:, 1]
+    mine = ((dst >= lo) & (dst < hi)).astype(np.int64)
+    mark = np.zeros(n, np.int64)
+    remote = (src < lo) | (src >= hi)
+    mark[src[(mine == 1) & remote]] = 1
+    mine_incl, mark_incl = np.cumsum(mine), np.cumsum(mark)
+    e_loc = int(mine_incl[-1]) if len(mine_incl) else 0
+    n_halo = int(mark_incl[-1]) if n else 0
+    eid = np.empty(e_loc, np.int64)
+    dl = np.empty(e_loc, np.int64)
+    cl = np.empty(e_loc, np.int64)
+    for e in range(len(edges)):
+        prev = mine_incl[e - 1] if e else 0
+        if mine_incl[e] == prev:
+            continue
+        p = mine_incl[e] - 1
+        eid[p] = e
+        dl[p] = dst[e] - lo
+        cl[p] = (hi - lo) + mark_incl[src[e]] - 1 if remote[e] else src[e] - lo
+    halo = np.empty(n_halo, np.int64)
+    for i in range(n):
+        prev = mark_incl[i - 1] if i else 0
+        if mark_incl[i] != prev:
+            halo[mark_incl[i] - 1] = i
+
+    def before(x):
+        x = min(max(x, 0), n)
+        return int(mark_incl[x - 1]) if x > 0 else 0
+    recv = [before(offsets[p + 1]) - before(offsets[p]) for p in range(len(offsets) - 1)]
+    return eid, dl, cl, halo, recv
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_halo_plan_model_equals_the_torch_construction(seed):
+    import torch
+    from pgl_b200.distributed.halo import HaloPlan, block_offsets
+    rng = np.random.default_rng(seed)
+    n, e, k = int(rng.integers(20, 400)), int(rng.integers(1, 3000)), int(rng.integers(1, 6))
+    edges = rng.integers(0, n, (e, 2)).astype(np.int64)
+    offsets = block_offsets(n, k)
+    if k > 2 and seed % 2:
+        offsets[2] = offsets[1]          # an empty part
+    for r in range(k):
+        lo, hi = offsets[r], offsets[r + 1]
+        eid, dl, cl, halo, recv = halo_plan_model(edges, n, lo, hi, offsets)
+        # world 1 per call (no collective): the torch-op construction the gloo tests use
+        src, dst = edges[:, 0], edges[:, 1]
+        w_eid = np.nonzero((dst >= lo) & (dst < hi))[0]
+        s = src[w_eid]
+        rem = (s < lo) | (s >= hi)
+        w_halo = np.unique(s[rem])
+        w_cl = np.where(rem, np.searchsorted(w_halo, s) + (hi - lo), s - lo)
+        assert (eid == w_eid).all() and (dl == dst[w_eid] - lo).all() and (cl == w_cl).all() and (halo == w_halo).all()
+        assert recv == [int(((w_halo >= offsets[p]) & (w_halo < offsets[p + 1])).sum()) for p in range(k)]
+    plan = HaloPlan.build(torch.from_numpy(edges), n, [0, n], 0, 1)
+    eid, dl, cl, halo, recv = halo_plan_model(edges, n, 0, n, [0, n])
+    assert (plan.eid.numpy() == eid).all() and (plan.col_local.numpy() == cl).all() and plan.n_halo == 0 == len(halo)
