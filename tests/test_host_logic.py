@@ -184,3 +184,32 @@ def test_bench_balanced_row_bounds():
     assert bench.block_bounds(10, 4, 0) == (0, 3) and bench.block_bounds(10, 4, 3) == (8, 10)
     assert bench.parse_grid(type("A", (), {"grid": ""})(), 8) == (8, 1)
     assert bench.parse_grid(type("A", (), {"grid": "2x4"})(), 8) == (2, 4)
+
+
+def test_sampling_subgraph_matches_reference_relabelling():
+    """pgl.sampling.subgraph (reference pgl/sampling/custom.py:23-83): edges renumbered exactly as the reference's
+    compiled map_edges does with the {node: position} dict, features sliced by nodes / eid."""
+    import pgl_b200 as pgl
+    from oracle import build as obuild
+    rng = np.random.default_rng(0)
+    n = 30
+    edges = rng.integers(0, n, (60, 2)).astype(np.int64)
+    g = pgl.Graph(edges=edges, num_nodes=n, node_feat={"x": rng.standard_normal((n, 3)).astype(np.float32)},
+                  edge_feat={"w": rng.standard_normal((60, 2)).astype(np.float32)})
+    nodes = rng.permutation(n)[:20]
+    eid = np.flatnonzero(np.isin(edges[:, 0], nodes) & np.isin(edges[:, 1], nodes))
+    sg = pgl.sampling.subgraph(g, nodes, eid=eid)
+    reindex = {int(v): i for i, v in enumerate(nodes)}
+    want = np.array([[reindex[int(a)], reindex[int(b)]] for a, b in edges[eid]])
+    assert (np.asarray(sg.edges) == want).all() and sg.num_nodes == 20
+    assert (sg.node_feat["x"] == g.node_feat["x"][nodes]).all() and (sg.edge_feat["w"] == g.edge_feat["w"][eid]).all()
+    gk = obuild.load_ref_graph_kernel()
+    if gk is not None:
+        ref = np.asarray(gk.map_edges(np.arange(len(eid), dtype=np.int64), edges[eid], reindex))
+        assert (ref == np.asarray(sg.edges)).all()
+    sg2 = pgl.sampling.subgraph(g, nodes, edges=edges[eid], with_edge_feat=False)
+    assert (np.asarray(sg2.edges) == want).all() and not sg2.edge_feat
+    with pytest.raises(ValueError):
+        pgl.sampling.subgraph(g, nodes)
+    with pytest.raises(ValueError):
+        pgl.sampling.subgraph(g, nodes, edges=edges[eid])      # edge features need eid
